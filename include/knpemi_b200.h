@@ -1,0 +1,150 @@
+/*
+ * knpemi_b200.h -- C ABI of libknpemi_b200.so, the B200 (sm_100a) backend of the
+ * membrane-ODE stage of knpemi.
+ *
+ * This is the drop-in boundary.  Each entry point names the
+ * piece of the reference's MembraneModel (src/knpemi/odeSolver.py, cited as
+ * odeSolver.py:LINE) it replaces.  Plain pointers and sizes only: host buffers
+ * are caller-owned and may come from NumPy (`arr.ctypes.data`), DLPack or
+ * kem_host_alloc().  Every function returns 0 on success, a negative KEM_E_*
+ * code on argument / CUDA errors (text via kem_last_error()), and kem_step*
+ * return KEM_NONFINITE (> 0) when an integrated state is not finite -- the
+ * counterpart of the reference's `assert success` (odeSolver.py:121).
+ *
+ * There is no CPU fallback: without a CUDA device kem_create() fails.
+ * Thread-safety: one host thread per handle.
+ */
+#ifndef KNPEMI_B200_H
+#define KNPEMI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KEM_OK 0
+#define KEM_NONFINITE 1
+#define KEM_E_ARG (-1)
+#define KEM_E_CUDA (-2)
+#define KEM_E_MODEL (-3)
+#define KEM_E_NOMEM (-4)
+
+#define KEM_STATE 0      /* `what == 'state'`     odeSolver.py:133 */
+#define KEM_PARAM 1      /* `what == 'parameter'` odeSolver.py:134 */
+
+#define KEM_SCHEME_RK4 0 /* scheme O1: classical RK4, n_sub sub-steps + current epilogue */
+
+typedef struct kem_handle_s *kem_handle;
+
+typedef struct kem_model_info {
+    int ns;          /* states per DOF        (len(init_state_values()),     odeSolver.py:41) */
+    int np;          /* parameters per DOF    (len(init_parameter_values()), odeSolver.py:42) */
+    int n_out;       /* parameter slots the RHS writes (I_ch_*; mm_hh.py:220-225) */
+    int n_used;      /* parameter slots the RHS reads */
+    int n_tslots;    /* host-evaluated time-only factors per stage time */
+    int out_cols[16];
+    char name[64];
+    char source_hash[32];
+} kem_model_info;
+
+typedef struct kem_step_times {
+    double ms_h2d;      /* host->device copies of the step's input columns  */
+    double ms_kernel;   /* fused step kernel, max over the handle's devices */
+    double ms_d2h;      /* device->host copies of the step's output columns */
+    double ms_total;    /* first copy enqueued -> last copy landed, max over devices */
+} kem_step_times;
+
+/* one column moved by kem_step_io(): table[:, col] <-> host[0:n_dof] */
+typedef struct kem_io_column {
+    int kind;        /* KEM_STATE | KEM_PARAM */
+    int col;
+    double *host;    /* n_dof doubles */
+} kem_io_column;
+
+/* ---- library ---------------------------------------------------------------- */
+int kem_version(void);
+const char *kem_last_error(void);
+int kem_device_count(int *n_out);
+
+/* ---- models: replaces `ode.rhs_numba.address` (odeSolver.py:96) -------------- */
+/* Load a generated model library (knpemi_b200.codegen) and register it. */
+int kem_model_load(const char *so_path, int *model_id_out);
+int kem_model_find(const char *name_or_hash, int *model_id_out);
+int kem_model_get_info(int model_id, kem_model_info *out);
+/* registers/thread and resident blocks/SM of the model's step kernel on device `dev` */
+int kem_model_launch_info(int model_id, int dev, int block, int *regs_out, int *blocks_per_sm_out);
+
+/* ---- construction: MembraneModel.__init__ (odeSolver.py:8-49) ---------------- */
+/* Allocates the SoA tables for n_dof DOFs, split in contiguous ranges over the
+ * n_dev devices dev_ids[] (NULL = device 0), every row initialised to the
+ * model defaults (odeSolver.py:41-42). */
+int kem_create(int model_id, int64_t n_dof, int n_dev, const int *dev_ids,
+               const double *state_defaults, const double *param_defaults, kem_handle *out);
+int kem_destroy(kem_handle h);
+int kem_n_dof(kem_handle h, int64_t *n_out);
+/* DOF range [begin, end) owned by the k-th device of the handle */
+int kem_shard_range(kem_handle h, int k, int *dev_out, int64_t *begin_out, int64_t *end_out);
+
+/* ---- table access: __set_ODE / __get_PDE / __set_ODE_values ------------------- */
+/* table[:, col] = v for every DOF (odeSolver.py:183-187 with a constant value and no locator) */
+int kem_set_uniform(kem_handle h, int kind, int col, double v);
+/* table[:, col] = host_src[0:n]                      (odeSolver.py:142-144, locator None) */
+int kem_set_column(kem_handle h, int kind, int col, const double *host_src, int64_t n);
+/* table[mask, col] = host_src[mask]                  (odeSolver.py:138-144 with a locator) */
+int kem_set_column_masked(kem_handle h, int kind, int col, const double *host_src,
+                          const uint8_t *host_mask, int64_t n);
+/* table[mask, col] = v                               (odeSolver.py:183-187, constant value) */
+int kem_set_value_masked(kem_handle h, int kind, int col, double v, const uint8_t *host_mask,
+                         int64_t n);
+/* host_dst[0:n] = table[:, col]                      (odeSolver.py:159-164) */
+int kem_get_column(kem_handle h, int kind, int col, double *host_dst, int64_t n);
+/* 1 if the column is stored as one value for all DOFs */
+int kem_column_is_uniform(kem_handle h, int kind, int col, int *is_uniform_out, double *value_out);
+
+/* ---- stimulus mask: `stimulus_mask` of step_lsoda (odeSolver.py:98-100) ------- */
+/* Upload the 0/1 mask used by the next kem_step calls; NULL = every DOF (the
+ * reference's default locator `lambda x: True`). */
+int kem_set_stimulus_mask(kem_handle h, const uint8_t *host_mask_or_null, int64_t n);
+
+/* ---- the step: MembraneModel.step_lsoda row loop (odeSolver.py:106-123) ------- */
+/* Advance every DOF from t0 to t0+dt.  The n_stim (column, value) pairs are the
+ * `stimulus` dict, written stickily into the parameter table under the current
+ * stimulus mask (odeSolver.py:110-112).  status_flags != NULL: wait for the
+ * kernel and report (bit 0: non-finite state); NULL: enqueue only, errors
+ * surface at the next synchronising call. */
+int kem_step(kem_handle h, double t0, double dt, int n_sub, int scheme,
+             int n_stim, const int *stim_cols, const double *stim_vals, int *status_flags);
+/* same, timed with CUDA events on the launching streams */
+int kem_step_timed(kem_handle h, double t0, double dt, int n_sub, int scheme,
+                   int n_stim, const int *stim_cols, const double *stim_vals,
+                   int *status_flags, kem_step_times *times_out);
+/* One coupled PDE/ODE exchange (utils.py:217-233 + step + run_2D.py:105-109):
+ * copy n_in host columns in, step, copy n_out host columns out, pipelined in
+ * DOF chunks over each device's streams.  Synchronous. */
+int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme,
+                int n_stim, const int *stim_cols, const double *stim_vals,
+                int n_in, const kem_io_column *in, int n_out, const kem_io_column *out,
+                int *status_flags, kem_step_times *times_out);
+int kem_sync(kem_handle h);
+/* launch configuration knobs: threads per block (64/128/256; 0 = model default) */
+int kem_set_block(kem_handle h, int block);
+/* number of kernels this handle has launched since creation */
+int kem_launch_count(kem_handle h, int64_t *n_out);
+
+/* ---- pinned host memory for callers that want zero-staging transfers ---------- */
+int kem_host_alloc(void **ptr_out, size_t bytes);
+int kem_host_free(void *ptr);
+
+/* ---- measurement helpers ------------------------------------------------------ */
+/* Dependent-chain-free DFMA micro-benchmark: the measured FP64 pipe peak of
+ * device `dev` in TFLOP/s (2 flops per DFMA), used as roofline denominator. */
+int kem_fp64_peak(int dev, double *tflops_out, double *ms_out);
+/* Device-to-device copy bandwidth of device `dev` in GB/s (read + write bytes). */
+int kem_hbm_copy_peak(int dev, double *gbs_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KNPEMI_B200_H */

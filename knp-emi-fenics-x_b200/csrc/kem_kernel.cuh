@@ -1,0 +1,239 @@
+// kem_kernel.cuh -- the fused membrane-ODE step kernel (sm_100a), generic over
+// a generated model struct M (see knpemi_b200/codegen/emit.py).
+//
+// One thread advances one membrane DOF by one PDE step.  It replaces the row
+// loop of MembraneModel.step_lsoda (reference src/knpemi/odeSolver.py:107-122):
+//   * sticky stimulus write into the parameter table        (odeSolver.py:110-112)
+//   * integration of the row from t0 to t0+dt               (odeSolver.py:116-120,
+//     here scheme O1: classical RK4, n_sub sub-steps)
+//   * the RHS side effect that leaves I_ch_* in parameter slots (mm_hh.py:220-225),
+//     evaluated once at (t0+dt, y_end)
+//   * write-back of the row                                  (odeSolver.py:122)
+//
+// Data layout: structure-of-arrays, one contiguous double column per state /
+// per-DOF parameter / output slot, so a warp's 32 loads of one column are one
+// 256-byte coalesced request.  Each column is read once and written once per
+// PDE step; all states stay in registers across the 4*n_sub+1 RHS evaluations.
+// Parameters that are uniform over the DOFs are read through a zero index mask
+// (one broadcast transaction) from a small per-device table.
+//
+// Binding roofline: the FP64 pipe (about 25k DFMA-class instructions against
+// 144 bytes per DOF-step for the HH models) -- see DESIGN.md.
+#pragma once
+#include "kem_model_api.h"
+
+template <class M>
+struct KemArgs {
+    long long n;
+    double *y[M::NS];
+    const double *p[M::NP];
+    long long pmask[M::NP];
+    double *out[M::NOUT > 0 ? M::NOUT : 1];
+    const unsigned char *stim_mask;
+    int n_stim;
+    int stim_col[KEM_MAX_STIM];
+    double stim_val[KEM_MAX_STIM];
+    double *stim_ptr[KEM_MAX_STIM];
+    const double *ttab;
+    int n_sub;
+    double h;
+    int *flags;
+};
+
+template <class M, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+kem_step_kernel(const __grid_constant__ KemArgs<M> a)
+{
+    constexpr int NS = M::NS, NP = M::NP, NOUT = M::NOUT, NT = M::NT;
+    extern __shared__ double s_tt[];
+
+    // time-only factors of every stage time of this PDE step (host-evaluated)
+    if (NT > 0) {
+        const int n_tt = (2 * a.n_sub + 2) * NT;
+        for (int k = threadIdx.x; k < n_tt; k += BLOCK) s_tt[k] = a.ttab[k];
+        __syncthreads();
+    }
+
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= a.n) return;
+
+    // ---- parameters of this DOF (only the slots the RHS reads)
+    double p[NP];
+#pragma unroll
+    for (int c = 0; c < NP; ++c)
+        p[c] = M::used(c) ? __ldg(a.p[c] + (i & a.pmask[c])) : 0.0;
+
+    // ---- sticky stimulus (odeSolver.py:110-112)
+    if (a.n_stim > 0 && a.stim_mask[i]) {
+#pragma unroll
+        for (int s = 0; s < KEM_MAX_STIM; ++s) {
+            if (s < a.n_stim) {
+                const int col = a.stim_col[s];
+                const double v = a.stim_val[s];
+#pragma unroll
+                for (int c = 0; c < NP; ++c)
+                    if (M::used(c) && c == col) p[c] = v;
+                a.stim_ptr[s][i] = v;
+            }
+        }
+    }
+
+    // ---- parameter-only sub-expressions, once per PDE step
+    typename M::H q;
+    M::hoist(p, q);
+
+    double y[NS];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) y[c] = a.y[c][i];
+
+    const double h = a.h;
+    const double hh = 0.5 * h;
+    const double h6 = h / 6.0;
+
+    // ---- classical RK4, association identical to oracle/knpemi_oracle.c:step_row
+#pragma unroll 1
+    for (int j = 0; j < a.n_sub; ++j) {
+        const double *ta = s_tt + (2 * j) * NT;
+        const double *tb = ta + NT;
+        const double *tc = tb + NT;
+        double k[NS], w[NS], acc[NS];
+
+        M::deriv(y, k, q, ta);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) { acc[c] = k[c]; w[c] = y[c] + hh * k[c]; }
+
+        M::deriv(w, k, q, tb);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) { acc[c] = acc[c] + 2.0 * k[c]; w[c] = y[c] + hh * k[c]; }
+
+        M::deriv(w, k, q, tb);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) { acc[c] = acc[c] + 2.0 * k[c]; w[c] = y[c] + h * k[c]; }
+
+        M::deriv(w, k, q, tc);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) y[c] = y[c] + h6 * (acc[c] + k[c]);
+    }
+
+    // ---- current epilogue: I_ch(y(t0+dt)) into the output parameter slots
+    if (NOUT > 0) {
+        double o[NOUT > 0 ? NOUT : 1];
+        M::outputs(y, o, q, s_tt + (2 * a.n_sub + 1) * NT);
+#pragma unroll
+        for (int c = 0; c < NOUT; ++c) a.out[c][i] = o[c];
+    }
+
+    bool finite = true;
+#pragma unroll
+    for (int c = 0; c < NS; ++c) {
+        a.y[c][i] = y[c];
+        finite = finite && isfinite(y[c]);
+    }
+    if (!finite) atomicOr(a.flags, 1);
+}
+
+template <class M, int BLOCK>
+static cudaError_t kem_launch_block(const KemArgs<M> &a, size_t smem, cudaStream_t stream)
+{
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kem_step_kernel<M, BLOCK>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    const long long grid = (a.n + BLOCK - 1) / BLOCK;
+    kem_step_kernel<M, BLOCK><<<(unsigned)grid, BLOCK, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <class M>
+static cudaError_t kem_launch(const KemLaunch *L, cudaStream_t stream)
+{
+    if (L->n <= 0) return cudaSuccess;
+    if (L->n_stim > KEM_MAX_STIM || L->n_sub < 1) return cudaErrorInvalidValue;
+    if ((L->n + 63) / 64 > 0x7fffffffLL) return cudaErrorInvalidValue;
+    KemArgs<M> a;
+    a.n = L->n;
+    for (int c = 0; c < M::NS; ++c) a.y[c] = L->y[c];
+    for (int c = 0; c < M::NP; ++c) { a.p[c] = L->p[c]; a.pmask[c] = L->pmask[c]; }
+    for (int c = 0; c < M::NOUT; ++c) a.out[c] = L->out[c];
+    a.stim_mask = L->stim_mask;
+    a.n_stim = L->stim_mask ? L->n_stim : 0;
+    for (int s = 0; s < KEM_MAX_STIM; ++s) {
+        a.stim_col[s] = L->stim_col[s];
+        a.stim_val[s] = L->stim_val[s];
+        a.stim_ptr[s] = L->stim_ptr[s];
+    }
+    a.ttab = L->ttab;
+    a.n_sub = L->n_sub;
+    a.h = L->h;
+    a.flags = L->flags;
+    const size_t smem = (size_t)(2 * L->n_sub + 2) * M::NT * sizeof(double);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    const int block = L->block ? L->block : M::DEFAULT_BLOCK;
+    switch (block) {
+        case 64:  return kem_launch_block<M, 64>(a, smem, stream);
+        case 128: return kem_launch_block<M, 128>(a, smem, stream);
+        case 256: return kem_launch_block<M, 256>(a, smem, stream);
+        default:  return cudaErrorInvalidValue;
+    }
+}
+
+template <class M>
+static cudaError_t kem_launch_info(int *regs, int *max_blocks_per_sm, int block)
+{
+    cudaFuncAttributes fa;
+    cudaError_t e;
+    if (block == 0) block = M::DEFAULT_BLOCK;
+    int nb = 0;
+    switch (block) {
+        case 64:
+            e = cudaFuncGetAttributes(&fa, kem_step_kernel<M, 64>);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kem_step_kernel<M, 64>, 64, 0);
+            break;
+        case 128:
+            e = cudaFuncGetAttributes(&fa, kem_step_kernel<M, 128>);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kem_step_kernel<M, 128>, 128, 0);
+            break;
+        case 256:
+            e = cudaFuncGetAttributes(&fa, kem_step_kernel<M, 256>);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kem_step_kernel<M, 256>, 256, 0);
+            break;
+        default: return cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return e;
+    *regs = fa.numRegs;
+    *max_blocks_per_sm = nb;
+    return cudaSuccess;
+}
+
+// device-side numpy.mod (only reached if a model takes mod of a state-dependent value)
+__device__ __forceinline__ double kem_npmod(double a, double b)
+{
+    double r = fmod(a, b);
+    if (r != 0.0) {
+        if ((b < 0.0) != (r < 0.0)) r += b;
+    } else {
+        r = copysign(0.0, b);
+    }
+    return r;
+}
+
+static inline double kem_npmod_host(double a, double b)
+{
+    double r = fmod(a, b);
+    if (r != 0.0) {
+        if ((b < 0.0) != (r < 0.0)) r += b;
+    } else {
+        r = copysign(0.0, b);
+    }
+    return r;
+}
+
+#define KEM_DEFINE_MODEL(M, NAME_STR, HASH_STR, OUT_COLS, USED_COLS, N_USED)                  \
+    extern "C" __attribute__((visibility("default"))) const KemModelDesc *kem_model_descriptor(void) \
+    {                                                                                         \
+        static KemModelDesc d = {KEM_MODEL_ABI_VERSION, NAME_STR, HASH_STR, M::NS, M::NP,     \
+                                 M::NOUT, OUT_COLS, N_USED, USED_COLS, M::NT,                 \
+                                 &M::tonly, &kem_launch<M>, 0, &kem_launch_info<M>};          \
+        return &d;                                                                            \
+    }

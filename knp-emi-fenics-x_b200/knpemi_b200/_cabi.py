@@ -1,0 +1,178 @@
+"""ctypes binding of libknpemi_b200.so (C ABI: include/knpemi_b200.h).
+
+This is the thin layer the north star asks for: NumPy buffers are passed as raw
+pointers (``arr.ctypes.data``); there is no PyTorch and no CPU fallback -- if the
+shared library is missing or no CUDA device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .codegen.build import RUNTIME_LIB
+
+KEM_STATE, KEM_PARAM = 0, 1
+KEM_SCHEME_RK4 = 0
+KEM_NONFINITE = 1
+KEM_MAX_STIM = 4
+
+
+class KemError(RuntimeError):
+    """Argument / CUDA / model error reported by libknpemi_b200."""
+
+
+class NonFiniteStateError(AssertionError):
+    """A membrane state became non-finite during a step.
+
+    Subclass of AssertionError: the reference signals integration failure with
+    ``assert success`` (src/knpemi/odeSolver.py:121)."""
+
+
+class kem_model_info(C.Structure):
+    _fields_ = [("ns", C.c_int), ("np", C.c_int), ("n_out", C.c_int), ("n_used", C.c_int),
+                ("n_tslots", C.c_int), ("out_cols", C.c_int * 16), ("name", C.c_char * 64),
+                ("source_hash", C.c_char * 32)]
+
+
+class kem_step_times(C.Structure):
+    _fields_ = [("ms_h2d", C.c_double), ("ms_kernel", C.c_double), ("ms_d2h", C.c_double),
+                ("ms_total", C.c_double)]
+
+
+class kem_io_column(C.Structure):
+    _fields_ = [("kind", C.c_int), ("col", C.c_int), ("host", C.c_void_p)]
+
+
+_DP = C.POINTER(C.c_double)
+_U8P = C.POINTER(C.c_uint8)
+_IP = C.POINTER(C.c_int)
+_H = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/knpemi_b200.h declares
+SIGNATURES = {
+    "kem_version": (C.c_int, []),
+    "kem_last_error": (C.c_char_p, []),
+    "kem_device_count": (C.c_int, [_IP]),
+    "kem_model_load": (C.c_int, [C.c_char_p, _IP]),
+    "kem_model_find": (C.c_int, [C.c_char_p, _IP]),
+    "kem_model_get_info": (C.c_int, [C.c_int, C.POINTER(kem_model_info)]),
+    "kem_model_launch_info": (C.c_int, [C.c_int, C.c_int, C.c_int, _IP, _IP]),
+    "kem_create": (C.c_int, [C.c_int, C.c_int64, C.c_int, _IP, _DP, _DP, C.POINTER(_H)]),
+    "kem_destroy": (C.c_int, [_H]),
+    "kem_n_dof": (C.c_int, [_H, C.POINTER(C.c_int64)]),
+    "kem_shard_range": (C.c_int, [_H, C.c_int, _IP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "kem_set_uniform": (C.c_int, [_H, C.c_int, C.c_int, C.c_double]),
+    "kem_set_column": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
+    "kem_set_column_masked": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
+    "kem_set_value_masked": (C.c_int, [_H, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int64]),
+    "kem_get_column": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
+    "kem_column_is_uniform": (C.c_int, [_H, C.c_int, C.c_int, _IP, _DP]),
+    "kem_set_stimulus_mask": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "kem_step": (C.c_int, [_H, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _IP, _DP, _IP]),
+    "kem_step_timed": (C.c_int, [_H, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _IP, _DP, _IP,
+                                 C.POINTER(kem_step_times)]),
+    "kem_step_io": (C.c_int, [_H, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _IP, _DP,
+                              C.c_int, C.POINTER(kem_io_column), C.c_int, C.POINTER(kem_io_column),
+                              _IP, C.POINTER(kem_step_times)]),
+    "kem_sync": (C.c_int, [_H]),
+    "kem_set_block": (C.c_int, [_H, C.c_int]),
+    "kem_launch_count": (C.c_int, [_H, C.POINTER(C.c_int64)]),
+    "kem_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "kem_host_free": (C.c_int, [C.c_void_p]),
+    "kem_fp64_peak": (C.c_int, [C.c_int, _DP, _DP]),
+    "kem_hbm_copy_peak": (C.c_int, [C.c_int, _DP]),
+}
+
+_lib = None
+
+
+def library_path() -> str:
+    return os.environ.get("KNPEMI_B200_LIB", RUNTIME_LIB)
+
+
+def lib() -> C.CDLL:
+    """Load libknpemi_b200.so (built by ``__graft_entry__.build()``); raises if absent."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise KemError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; "
+                           "g.build()'` (there is no CPU fallback)")
+        L = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> int:
+    if rc == 0:
+        return 0
+    msg = lib().kem_last_error().decode(errors="replace")
+    if rc == KEM_NONFINITE:
+        raise NonFiniteStateError(msg or "non-finite membrane state")
+    raise KemError(f"{what or 'libknpemi_b200'} failed (code {rc}): {msg}")
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = lib().kem_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def load_model(so_path: str) -> int:
+    mid = C.c_int(-1)
+    check(lib().kem_model_load(so_path.encode(), C.byref(mid)), "kem_model_load")
+    return mid.value
+
+
+def model_info(model_id: int) -> kem_model_info:
+    info = kem_model_info()
+    check(lib().kem_model_get_info(model_id, C.byref(info)), "kem_model_get_info")
+    return info
+
+
+def ptr(a: np.ndarray) -> int:
+    """Raw data pointer of a C-contiguous array (caller keeps it alive)."""
+    assert a.flags.c_contiguous
+    return a.ctypes.data
+
+
+class PinnedArray:
+    """1-D float64 / uint8 NumPy view over page-locked memory from kem_host_alloc."""
+
+    def __init__(self, n: int, dtype=np.float64):
+        self.dtype = np.dtype(dtype)
+        self.nbytes = max(int(n) * self.dtype.itemsize, 8)
+        p = C.c_void_p()
+        check(lib().kem_host_alloc(C.byref(p), self.nbytes), "kem_host_alloc")
+        self._ptr = p.value
+        buf = (C.c_char * self.nbytes).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(n))
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            lib().kem_host_free(C.c_void_p(self._ptr))
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def fp64_peak(dev: int = 0) -> tuple[float, float]:
+    tf, ms = C.c_double(), C.c_double()
+    check(lib().kem_fp64_peak(dev, C.byref(tf), C.byref(ms)), "kem_fp64_peak")
+    return tf.value, ms.value
+
+
+def hbm_copy_peak(dev: int = 0) -> float:
+    g = C.c_double()
+    check(lib().kem_hbm_copy_peak(dev, C.byref(g)), "kem_hbm_copy_peak")
+    return g.value

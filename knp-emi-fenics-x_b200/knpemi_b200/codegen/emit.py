@@ -1,0 +1,320 @@
+"""Expression DAG -> CUDA C++ source of one model library.
+
+The emitted translation unit defines ``struct Model`` with
+
+* ``hoist(p, q)``      parameter-only nodes, once per DOF per PDE step (device)
+* ``deriv(y, dy, q, ts)``   state derivatives, straight-line fp64 (device)
+* ``outputs(y, o, q, ts)``  the parameter slots the reference RHS writes as a side
+  effect -- the channel currents ``I_ch_*`` (mm_hh.py:220-225)            (device)
+* ``tonly(t, ts)``     time-only nodes, evaluated with glibc on the host
+
+and instantiates the generic fused kernel of ``csrc/kem_kernel.cuh`` for it.
+Every arithmetic node is emitted as exactly one C++ operation on named
+temporaries in the association the Python source has, constants as hex-float
+literals, so the only differences to the reference's compiled cfunc are FMA
+contraction by nvcc and CUDA's libm (both <= 1 ulp per operation).
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+from dataclasses import dataclass
+
+from .ir import P, S, T, Dag, ModelSourceError
+from .parse import ParsedModel
+
+CODEGEN_VERSION = "3"
+
+
+@dataclass
+class EmitOptions:
+    default_block: int = 128
+    #: 0 = every operation as written; 1 = divisions by constants become
+    #: multiplications by the rounded reciprocal (<= 1 ulp per division)
+    fast_const_div: int = 0
+
+
+@dataclass
+class EmittedModel:
+    name: str
+    source: str
+    source_hash: str
+    ns: int
+    np: int
+    out_cols: list
+    used_cols: list
+    n_tslots: int
+    n_hoisted: int
+    stats: dict
+
+
+def _lit(v: float) -> str:
+    if math.isnan(v) or math.isinf(v):
+        raise ModelSourceError("non-finite constant in model expression")
+    s = float(v).hex()
+    return f"({s})" if s.startswith("-") else s
+
+
+class _Emitter:
+    def __init__(self, pm: ParsedModel, ns: int, np_: int, opts: EmitOptions):
+        self.pm, self.dag, self.ns, self.np, self.opts = pm, pm.dag, ns, np_, opts
+        for c in pm.dy:
+            if not 0 <= c < ns:
+                raise ModelSourceError(f"values[{c}] outside the {ns} states of the model")
+        missing = sorted(set(range(ns)) - set(pm.dy))
+        if missing:
+            raise ModelSourceError(f"right-hand side never assigns values{missing}")
+        for c in pm.out:
+            if not 0 <= c < np_:
+                raise ModelSourceError(f"parameters[{c}] outside the {np_} parameters of the model")
+        self.out_cols = sorted(pm.out)
+
+    # ------------------------------------------------------------------ naming
+    def nm(self, nid: int) -> str:
+        return f"v{nid}"
+
+    def comment(self, nid: int) -> str:
+        name = self.dag.names.get(nid)
+        return f"  // {name}" if name else ""
+
+    # ------------------------------------------------------- where a node lives
+    def klass(self, nid: int) -> str:
+        d = self.dag.deps[nid]
+        if not d:
+            return "const"
+        if d == frozenset(P):
+            return "hoist"
+        if d == frozenset(T):
+            return "time"
+        return "dyn"
+
+    def operand(self, nid: int, ctx: str) -> str:
+        """C++ text for reading node ``nid`` from code section ``ctx``."""
+        n = self.dag.nodes[nid]
+        if n.op == "const":
+            return _lit(n.val)
+        if n.op == "iconst":
+            return _lit(float(n.val))
+        k = self.klass(nid)
+        if ctx == "dyn":
+            if n.op == "state":
+                return f"y[{n.val}]"
+            if k == "hoist":
+                return f"q.{self.nm(nid)}"
+            if k == "time":
+                return f"ts[{self.tslot[nid]}]"
+            return self.nm(nid)
+        if ctx == "hoist":
+            if n.op == "param":
+                return f"p[{n.val}]"
+            return self.nm(nid)
+        if ctx == "time":
+            if n.op == "time":
+                return "t"
+            return self.nm(nid)
+        raise AssertionError(ctx)
+
+    def rhs_text(self, nid: int, ctx: str) -> str:
+        n = self.dag.nodes[nid]
+        a = [self.operand(c, ctx) for c in n.args]
+        op = n.op
+        if op == "add":
+            return f"{a[0]} + {a[1]}"
+        if op == "sub":
+            return f"{a[0]} - {a[1]}"
+        if op == "mul":
+            return f"{a[0]} * {a[1]}"
+        if op == "div":
+            if self.opts.fast_const_div and self.dag.is_const(n.args[1]):
+                return f"{a[0]} * {_lit(1.0 / self.dag.fvalue(n.args[1]))}"
+            return f"{a[0]} / {a[1]}"
+        if op == "neg":
+            return f"-{a[0]}"
+        if op in ("exp", "log", "sqrt"):
+            return f"{op}({a[0]})"
+        if op == "pow":
+            return f"pow({a[0]}, {a[1]})"
+        if op == "mod":
+            return f"kem_npmod({a[0]}, {a[1]})" if ctx != "time" else f"kem_npmod_host({a[0]}, {a[1]})"
+        if op in ("lt", "le", "gt", "ge"):
+            sym = {"lt": "<", "le": "<=", "gt": ">", "ge": ">="}[op]
+            return f"(double)({a[0]} {sym} {a[1]})"
+        raise AssertionError(op)
+
+    def powi_lines(self, nid: int, ctx: str, indent: str) -> list:
+        """numba's exponentiation by squaring, one multiply per line."""
+        n = self.dag.nodes[nid]
+        e = int(n.val)
+        x = self.operand(n.args[0], ctx)
+        lines = []
+        neg = e < 0
+        e = abs(e)
+        if e == 0:
+            return [f"{indent}const double {self.nm(nid)} = 1.0;"]
+        r, a, k = None, x, 0
+        while e:
+            if e & 1:
+                if r is None:
+                    r = a
+                else:
+                    t = f"{self.nm(nid)}_r{k}"
+                    lines.append(f"{indent}const double {t} = {r} * {a};")
+                    r = t
+            e >>= 1
+            if e:
+                t = f"{self.nm(nid)}_s{k}"
+                lines.append(f"{indent}const double {t} = {a} * {a};")
+                a = t
+            k += 1
+        final = f"1.0 / {r}" if neg else r
+        lines.append(f"{indent}const double {self.nm(nid)} = {final};{self.comment(nid)}")
+        return lines
+
+    def section(self, order, ctx: str, indent: str = "        ") -> list:
+        lines = []
+        for nid in order:
+            n = self.dag.nodes[nid]
+            if n.op in ("const", "iconst", "param", "state", "time"):
+                continue
+            if self.klass(nid) != ctx:
+                continue
+            if n.op == "powi":
+                lines += self.powi_lines(nid, ctx, indent)
+            else:
+                lines.append(f"{indent}const double {self.nm(nid)} = {self.rhs_text(nid, ctx)};"
+                             f"{self.comment(nid)}")
+        return lines
+
+    # -------------------------------------------------------------------- emit
+    def emit(self, name: str) -> EmittedModel:
+        dag, pm = self.dag, self.pm
+        dy_roots = [pm.dy[c] for c in range(self.ns)]
+        out_roots = [pm.out[c] for c in self.out_cols]
+        order_dy = dag.reachable(dy_roots)
+        order_out = dag.reachable(out_roots)
+        order_all = dag.reachable(dy_roots + out_roots)
+
+        used_cols = sorted({dag.nodes[n].val for n in order_all if dag.nodes[n].op == "param"})
+        for c in used_cols:
+            if not 0 <= c < self.np:
+                raise ModelSourceError(f"parameters[{c}] outside the {self.np} parameters of the model")
+
+        # frontier: hoisted / time nodes a device "dyn" node (or an output root) reads directly
+        hoist_front, time_front = [], []
+
+        def note(nid):
+            k = self.klass(nid)
+            if k == "hoist" and nid not in hoist_front:
+                hoist_front.append(nid)
+            elif k == "time" and nid not in time_front:
+                time_front.append(nid)
+
+        for nid in order_all:
+            if self.klass(nid) == "dyn":
+                for c in dag.nodes[nid].args:
+                    note(c)
+        for r in dy_roots + out_roots:
+            note(r)
+        hoist_front.sort()
+        time_front.sort()
+        self.tslot = {nid: k for k, nid in enumerate(time_front)}
+
+        order_hoist = dag.reachable(hoist_front)
+        order_time = dag.reachable(time_front)
+
+        L = []
+        w = L.append
+        w(f"// GENERATED by knpemi_b200.codegen v{CODEGEN_VERSION} -- do not edit.")
+        w(f"// model {name!r} from {pm.source_file}:{pm.lineno}")
+        w(f"// options: default_block={self.opts.default_block} fast_const_div={self.opts.fast_const_div}")
+        w('#include <math.h>')
+        w('#include "kem_kernel.cuh"')
+        w("")
+        w("namespace {")
+        w("struct Model {")
+        w(f"    static constexpr int NS = {self.ns}, NP = {self.np}, NOUT = {len(self.out_cols)}, "
+          f"NT = {len(time_front)};")
+        w(f"    static constexpr int DEFAULT_BLOCK = {self.opts.default_block};")
+        cond = " || ".join(f"c == {c}" for c in used_cols) or "false"
+        w(f"    __host__ __device__ static constexpr bool used(int c) {{ return {cond}; }}")
+        w("")
+        w("    // parameter-only values handed from hoist() to the sub-step loop")
+        w("    struct H {")
+        if hoist_front:
+            for nid in hoist_front:
+                w(f"        double {self.nm(nid)};{self.comment(nid)}")
+        else:
+            w("        double unused;")
+        w("    };")
+        w("")
+        w("    static __device__ __forceinline__ void hoist(const double (&p)[NP], H &q)")
+        w("    {")
+        L.extend(self.section(order_hoist, "hoist"))
+        for nid in hoist_front:
+            w(f"        q.{self.nm(nid)} = {self.operand(nid, 'hoist')};")
+        if not hoist_front:
+            w("        q.unused = 0.0; (void)p;")
+        w("    }")
+        w("")
+        w("    static __device__ __forceinline__ void deriv(const double (&y)[NS], double (&dy)[NS],")
+        w("                                                 const H &q, const double *__restrict__ ts)")
+        w("    {")
+        w("        (void)q; (void)ts;")
+        L.extend(self.section(order_dy, "dyn"))
+        for c in range(self.ns):
+            w(f"        dy[{c}] = {self.operand(pm.dy[c], 'dyn')};")
+        w("    }")
+        w("")
+        w("    static __device__ __forceinline__ void outputs(const double (&y)[NS],")
+        w("                                                   double (&o)[NOUT > 0 ? NOUT : 1],")
+        w("                                                   const H &q, const double *__restrict__ ts)")
+        w("    {")
+        w("        (void)y; (void)q; (void)ts; (void)o;")
+        L.extend(self.section(order_out, "dyn"))
+        for k, c in enumerate(self.out_cols):
+            w(f"        o[{k}] = {self.operand(pm.out[c], 'dyn')};  // parameters[{c}]")
+        w("    }")
+        w("")
+        w("    // host: time-only factors at stage time t (glibc libm, like the reference cfunc)")
+        w("    static void tonly(double t, double *ts)")
+        w("    {")
+        w("        (void)t; (void)ts;")
+        L.extend(self.section(order_time, "time"))
+        for nid in time_front:
+            w(f"        ts[{self.tslot[nid]}] = {self.operand(nid, 'time')};")
+        w("    }")
+        w("};")
+        w("")
+        oc = ", ".join(map(str, self.out_cols)) or "0"
+        uc = ", ".join(map(str, used_cols)) or "0"
+        w(f"const int OUT_COLS[] = {{{oc}}};")
+        w(f"const int USED_COLS[] = {{{uc}}};")
+        w("}  // namespace")
+        w("")
+        body = "\n".join(L)
+        h = hashlib.sha256(body.encode()).hexdigest()[:16]
+        body += (f'\nKEM_DEFINE_MODEL(Model, "{name}", "{h}", OUT_COLS, USED_COLS, {len(used_cols)})\n')
+
+        def count(order, ctx):
+            c = {}
+            for nid in order:
+                n = dag.nodes[nid]
+                if n.op in ("const", "iconst", "param", "state", "time") or self.klass(nid) != ctx:
+                    continue
+                key = n.op
+                if n.op == "powi":
+                    e = abs(int(n.val))
+                    c["mul"] = c.get("mul", 0) + max(e.bit_length() - 1, 0) + max(bin(e).count("1") - 1, 0)
+                    continue
+                c[key] = c.get(key, 0) + 1
+            return c
+
+        stats = {"deriv": count(order_dy, "dyn"), "outputs": count(order_out, "dyn"),
+                 "hoist": count(order_hoist, "hoist"), "time": count(order_time, "time")}
+        return EmittedModel(name=name, source=body, source_hash=h, ns=self.ns, np=self.np,
+                            out_cols=self.out_cols, used_cols=used_cols, n_tslots=len(time_front),
+                            n_hoisted=len(hoist_front), stats=stats)
+
+
+def emit_model(pm: ParsedModel, name: str, ns: int, np_: int, opts: EmitOptions | None = None) -> EmittedModel:
+    return _Emitter(pm, ns, np_, opts or EmitOptions()).emit(name)

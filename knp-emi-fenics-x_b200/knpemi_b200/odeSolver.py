@@ -1,0 +1,526 @@
+"""Drop-in ``MembraneModel`` whose stepping backend is a fused sm_100a CUDA kernel.
+
+Mirrors the public interface of the reference's ``knpemi.odeSolver.MembraneModel``
+(src/knpemi/odeSolver.py:6-189) -- same constructor ``(ode, ft, tag, Q)``, same
+setters / getters over ``u.x.array``, same ``step_lsoda(dt, stimulus,
+stimulus_locator)`` call, same public attributes -- so ``utils.setup_membrane_model``
+(utils.py:105-148), ``utils.update_ode_variables`` (utils.py:210-235) and the run
+scripts' ``solve_odes`` (run_2D.py:80-111) work unmodified.
+
+What differs, deliberately (SURVEY.md sections 0 and 8):
+
+* tables live in B200 HBM as structure-of-arrays columns; ``.states`` and
+  ``.parameters`` are lazily synchronised views (:class:`TableView`), not ndarrays;
+* the per-row LSODA solve (odeSolver.py:116-120; numbalsoda, un-pinned) is replaced
+  by the fixed-step scheme O1: classical RK4 with ``n_sub`` sub-steps (default 25,
+  the reference's vestigial ``n_steps_ODE``, run_2D.py:176) and the channel currents
+  evaluated at ``(t+dt, y(t+dt))``;
+* model defaults are read once instead of N times (odeSolver.py:41-42), locator
+  masks are evaluated vectorised when that provably gives the per-row answer, and
+  cached per callable.
+
+There is no CPU path: construction raises if libknpemi_b200.so or a CUDA device
+is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import time as _time
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import (KEM_PARAM, KEM_SCHEME_RK4, KEM_STATE, KemError, NonFiniteStateError, check,
+                    kem_io_column, kem_step_times)
+from .codegen import EmitOptions, model_library
+
+__all__ = ["MembraneModel", "TableView", "KemError", "NonFiniteStateError"]
+
+_SAMPLE_ROWS = 24
+
+
+def _default_devices():
+    env = os.environ.get("KNPEMI_B200_DEVICES")
+    if env:
+        return [int(x) for x in env.split(",") if x.strip() != ""]
+    n = _cabi.device_count()
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    return [local_rank if 0 <= local_rank < max(n, 1) else 0]
+
+
+class TableView:
+    """Host-side view of a device-resident ``[N, ncols]`` table.
+
+    Indexing reads the touched columns from the device (``view[:, c]``,
+    ``view[rows, c]``, ``np.asarray(view)``); assignment writes them back.
+    This is what keeps ``membrane.states[:, idx]`` of
+    examples/calibrate_initial_conditions/run_calibration.py:68-82 working
+    without mirroring whole tables every step.
+    """
+
+    def __init__(self, model, kind, ncols):
+        self._m, self._kind, self._ncols = model, kind, ncols
+
+    # -- ndarray-like surface
+    @property
+    def shape(self):
+        return (self._m.nodes, self._ncols)
+
+    @property
+    def ndim(self):
+        return 2
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float64)
+
+    @property
+    def size(self):
+        return self._m.nodes * self._ncols
+
+    def __len__(self):
+        return self._m.nodes
+
+    def _cols(self, colkey):
+        if isinstance(colkey, (int, np.integer)):
+            c = int(colkey)
+            if c < 0:
+                c += self._ncols
+            if not 0 <= c < self._ncols:
+                raise IndexError(f"column {colkey} out of range for {self._ncols} columns")
+            return [c], True
+        if isinstance(colkey, slice):
+            return list(range(*colkey.indices(self._ncols))), False
+        idx = np.atleast_1d(np.asarray(colkey))
+        if idx.dtype == bool:
+            idx = np.nonzero(idx)[0]
+        return [int(c) % self._ncols if int(c) < 0 else int(c) for c in idx], False
+
+    def _split(self, key):
+        if isinstance(key, tuple):
+            if len(key) != 2:
+                raise IndexError("a table view takes [rows] or [rows, cols]")
+            return key
+        return key, slice(None)
+
+    def _fetch(self, cols):
+        out = np.empty((self._m.nodes, len(cols)), dtype=np.float64)
+        tmp = np.empty(self._m.nodes, dtype=np.float64)
+        for k, c in enumerate(cols):
+            self._m._get_column(self._kind, c, tmp)
+            out[:, k] = tmp
+        return out
+
+    def __getitem__(self, key):
+        rowkey, colkey = self._split(key)
+        cols, scalar_col = self._cols(colkey)
+        data = self._fetch(cols)
+        if scalar_col:
+            return data[:, 0][rowkey]
+        return data[rowkey]
+
+    def __setitem__(self, key, value):
+        rowkey, colkey = self._split(key)
+        cols, scalar_col = self._cols(colkey)
+        data = self._fetch(cols)
+        if scalar_col:
+            data[:, 0][rowkey] = value
+        else:
+            data[rowkey] = value
+        for k, c in enumerate(cols):
+            self._m._set_column(self._kind, c, np.ascontiguousarray(data[:, k]))
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._fetch(list(range(self._ncols)))
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def copy(self):
+        return self.__array__()
+
+    def __iter__(self):
+        return iter(self.__array__())
+
+    def __repr__(self):
+        return f"<TableView {'states' if self._kind == KEM_STATE else 'parameters'} {self.shape} on device>"
+
+
+class MembraneModel:
+    '''ODE on membrane defined by tagged facet function (B200 backend)'''
+
+    def __init__(self, ode, ft, tag, Q, *, devices=None, n_sub=25, scheme="rk4", block=0,
+                 verbose=True, strict_locators=False, emit_options: EmitOptions | None = None,
+                 nvcc_flags=()):
+        assert isinstance(tag, int)                                   # odeSolver.py:13
+
+        # all DOFs of the membrane function space are stepped (odeSolver.py:32-38; `ft` unused)
+        self.dof_locations = np.asarray(Q.tabulate_dof_coordinates())
+        self.indices = np.arange(len(self.dof_locations))
+        nodes = len(self.indices)
+        self.nodes = nodes
+
+        if scheme != "rk4":
+            raise ValueError(f"unknown scheme {scheme!r}; this backend implements 'rk4' (scheme O1)")
+        self.scheme = scheme
+        self.n_sub = int(n_sub)
+        self.verbose = bool(verbose)
+        self.strict_locators = bool(strict_locators)
+
+        # defaults are read once, not once per row (odeSolver.py:41-42)
+        y0 = np.ascontiguousarray(ode.init_state_values(), dtype=np.float64)
+        p0 = np.ascontiguousarray(ode.init_parameter_values(), dtype=np.float64)
+        self._ns, self._np = len(y0), len(p0)
+
+        # RHS -> CUDA (replaces `ode.rhs_numba.address`, odeSolver.py:96)
+        lib_path, emitted = model_library(ode, emit_options, extra_flags=tuple(nvcc_flags))
+        self._emitted = emitted
+        self._lib = _cabi.lib()
+        self._model_id = _cabi.load_model(lib_path)
+        info = _cabi.model_info(self._model_id)
+        if info.ns != self._ns or info.np != self._np:
+            raise KemError("generated model library does not match the model module's table sizes")
+        self.output_columns = [info.out_cols[k] for k in range(info.n_out)]
+
+        self.devices = list(devices) if devices is not None else _default_devices()
+        dev_arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        check(self._lib.kem_create(self._model_id, nodes, len(self.devices), dev_arr,
+                                   y0.ctypes.data_as(C.POINTER(C.c_double)),
+                                   p0.ctypes.data_as(C.POINTER(C.c_double)), C.byref(h)),
+              "kem_create")
+        self._h = h
+        if block:
+            check(self._lib.kem_set_block(self._h, int(block)), "kem_set_block")
+
+        self.states = TableView(self, KEM_STATE, self._ns)
+        self.parameters = TableView(self, KEM_PARAM, self._np)
+
+        self.tag = tag
+        self.ode = ode
+        self.prefix = ode.__name__
+        self.time = 0
+
+        self._mask_cache = {}          # id(locator) -> (locator, mask)
+        self._stim_mask_key = "unset"
+        self.last_step_times = None
+
+        if self.verbose:
+            print(f'\t{self.prefix} Number of ODE points on the membrane {nodes}')
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.kem_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- Setting ODE state/parameter based on a FEM function (odeSolver.py:52-58)
+    def set_state(self, which, u, locator=None):
+        '''Set ODE based on PDE function `u`'''
+        return self.__set_ODE('state', which, u, locator=locator)
+
+    def set_parameter(self, which, u, locator=None):
+        '''Set ODE based on PDE function `u`'''
+        return self.__set_ODE('parameter', which, u, locator=locator)
+
+    # --- Getting PDE state/parameter based on a FEM function (odeSolver.py:61-67)
+    def get_state(self, which, u, locator=None):
+        '''Set PDE function `u` based on ODE'''
+        return self.__get_PDE('state', which, u, locator=locator)
+
+    def get_parameter(self, which, u, locator=None):
+        '''Set PDE function `u` based on ODE'''
+        return self.__get_PDE('parameter', which, u, locator=locator)
+
+    # --- Setting ODE states/parameters to "constant" values at certain locations (:70-76)
+    def set_state_values(self, value_dict, locator=None):
+        ''' param_name -> (lambda x: value)'''
+        return self.__set_ODE_values('state', value_dict, locator=locator)
+
+    def set_parameter_values(self, value_dict, locator=None):
+        ''' param_name -> (lambda x: value)'''
+        return self.__set_ODE_values('parameter', value_dict, locator=locator)
+
+    # --- Convenience (odeSolver.py:79-89)
+    def set_membrane_potential(self, u, locator=None):
+        '''Update ODE potential from the PDE function'''
+        return self.set_state('V', u, locator=locator)
+
+    def get_membrane_potential(self, u, locator=None):
+        '''Update PDE potentials from the ODE solver'''
+        return self.get_state('V', u, locator=locator)
+
+    @property
+    def V_index(self):
+        return self.ode.state_indices('V')
+
+    # ---- ODE integration (odeSolver.py:92-127) ------
+    def step_lsoda(self, dt, stimulus, stimulus_locator=None):
+        '''Solve the ODEs forward by dt with optional stimulus.
+
+        Kept under the reference's name so `solve_odes` (run_2D.py:98) is
+        untouched; the integrator is the fixed-step scheme of :meth:`step`.'''
+        return self.step(dt, stimulus, stimulus_locator)
+
+    def step(self, dt, stimulus=None, stimulus_locator=None, n_sub=None, timed=False):
+        '''Advance every membrane DOF from `time` to `time + dt` on the GPU.'''
+        cols, vals, n_stim = self._prepare_stimulus(stimulus, stimulus_locator)
+        n_sub = self.n_sub if n_sub is None else int(n_sub)
+        if self.verbose:
+            print(f'\t{self.prefix} Stepping {self.nodes} ODEs')
+        t_begin = _time.perf_counter()
+        flags = C.c_int(0)
+        if timed:
+            times = kem_step_times()
+            rc = self._lib.kem_step_timed(self._h, float(self.time), float(dt), n_sub, KEM_SCHEME_RK4,
+                                          n_stim, cols, vals, C.byref(flags), C.byref(times))
+            self.last_step_times = {"ms_kernel": times.ms_kernel, "ms_total": times.ms_total,
+                                    "ms_h2d": times.ms_h2d, "ms_d2h": times.ms_d2h}
+        else:
+            rc = self._lib.kem_step(self._h, float(self.time), float(dt), n_sub, KEM_SCHEME_RK4,
+                                    n_stim, cols, vals, C.byref(flags))
+        check(rc, "kem_step")                                          # odeSolver.py:121
+        self.time = self.time + dt                                     # odeSolver.py:106,123
+        if self.verbose:
+            print(f'\t{self.prefix} Stepped {self.nodes} ODES in {_time.perf_counter() - t_begin}s')
+        return self.states
+
+    def step_async(self, dt, stimulus=None, stimulus_locator=None, n_sub=None):
+        '''Enqueue one step without waiting for it; errors surface at :meth:`synchronize`.'''
+        cols, vals, n_stim = self._prepare_stimulus(stimulus, stimulus_locator)
+        n_sub = self.n_sub if n_sub is None else int(n_sub)
+        check(self._lib.kem_step(self._h, float(self.time), float(dt), n_sub, KEM_SCHEME_RK4,
+                                 n_stim, cols, vals, None), "kem_step")
+        self.time = self.time + dt
+        return self.states
+
+    def synchronize(self):
+        check(self._lib.kem_sync(self._h), "kem_sync")
+
+    def step_exchange(self, dt, inputs, outputs, stimulus=None, stimulus_locator=None, n_sub=None):
+        '''One coupled PDE->ODE->PDE exchange in a single pipelined call.
+
+        `inputs`  : {("state"|"parameter", name): u or ndarray}  copied host->device
+        `outputs` : {("state"|"parameter", name): u or ndarray}  copied device->host
+        Equivalent to the setter calls of utils.update_ode_variables (utils.py:227-233),
+        `step_lsoda`, and the getter calls of solve_odes (run_2D.py:105-109).
+        Returns the CUDA-event timings of the exchange (ms).'''
+        cols, vals, n_stim = self._prepare_stimulus(stimulus, stimulus_locator)
+        n_sub = self.n_sub if n_sub is None else int(n_sub)
+        keep = []
+
+        def pack(spec, writable):
+            arr = (kem_io_column * max(len(spec), 1))()
+            for k, ((what, name), u) in enumerate(spec.items()):
+                kind, col = self._kind_col(what, name)
+                a = self._host_array(u, writable)
+                keep.append(a)
+                arr[k].kind, arr[k].col, arr[k].host = kind, col, a.ctypes.data
+            return arr
+
+        a_in, a_out = pack(inputs, False), pack(outputs, True)
+        flags = C.c_int(0)
+        times = kem_step_times()
+        rc = self._lib.kem_step_io(self._h, float(self.time), float(dt), n_sub, KEM_SCHEME_RK4,
+                                   n_stim, cols, vals, len(inputs), a_in, len(outputs), a_out,
+                                   C.byref(flags), C.byref(times))
+        check(rc, "kem_step_io")
+        self.time = self.time + dt
+        self.last_step_times = {"ms_kernel": times.ms_kernel, "ms_total": times.ms_total,
+                                "ms_h2d": times.ms_h2d, "ms_d2h": times.ms_d2h}
+        return self.last_step_times
+
+    # ------------------------------------------------------------------ helpers
+    def launch_count(self):
+        n = C.c_int64(0)
+        check(self._lib.kem_launch_count(self._h, C.byref(n)), "kem_launch_count")
+        return n.value
+
+    def launch_info(self, block=0):
+        regs, nb = C.c_int(0), C.c_int(0)
+        check(self._lib.kem_model_launch_info(self._model_id, self.devices[0], block,
+                                              C.byref(regs), C.byref(nb)), "kem_model_launch_info")
+        return {"registers_per_thread": regs.value, "blocks_per_sm": nb.value}
+
+    def _kind_col(self, what, which):
+        if what == 'state':
+            return KEM_STATE, self.ode.state_indices(which)
+        if what == 'parameter':
+            return KEM_PARAM, self.ode.parameter_indices(which)
+        raise KeyError(what)
+
+    def _host_array(self, u, writable):
+        a = u.x.array if hasattr(u, "x") else u
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous
+                and a.ndim == 1 and len(a) >= self.nodes and (a.flags.writeable or not writable)):
+            raise KemError("step_exchange needs 1-D contiguous float64 host arrays of length >= N")
+        return a
+
+    def _prepare_stimulus(self, stimulus, stimulus_locator):
+        if stimulus is None:
+            stimulus = {}                                              # odeSolver.py:94
+        if len(stimulus) > _cabi.KEM_MAX_STIM:
+            raise KemError(f"at most {_cabi.KEM_MAX_STIM} stimulus entries per step are supported")
+        mask = self._mask(stimulus_locator) if stimulus else None     # odeSolver.py:98-100
+        key = None if mask is None else id(mask)
+        if stimulus and key != self._stim_mask_key:
+            if mask is None:
+                check(self._lib.kem_set_stimulus_mask(self._h, None, 0), "kem_set_stimulus_mask")
+            else:
+                m8 = np.ascontiguousarray(mask, dtype=np.uint8)
+                check(self._lib.kem_set_stimulus_mask(self._h, m8.ctypes.data, self.nodes),
+                      "kem_set_stimulus_mask")
+            self._stim_mask_key = key
+            self._stim_mask_ref = mask
+        n = len(stimulus)
+        cols = (C.c_int * max(n, 1))()
+        vals = (C.c_double * max(n, 1))()
+        for k, (name, value) in enumerate(stimulus.items()):
+            cols[k] = self.ode.parameter_indices(name)                 # odeSolver.py:112
+            vals[k] = float(value)
+        return cols, vals, n
+
+    def _mask(self, locator):
+        '''Boolean row mask of a locator; None means every row (odeSolver.py:138-140).'''
+        if locator is None:
+            return None
+        hit = self._mask_cache.get(id(locator))
+        if hit is not None and hit[0] is locator:
+            return hit[1]
+        mask = self._rows_of(locator)
+        if mask.all():
+            mask = None        # every row selected: same as no locator
+        self._mask_cache[id(locator)] = (locator, mask)
+        return mask
+
+    def _sample_rows(self, n):
+        if n <= _SAMPLE_ROWS:
+            return np.arange(n)
+        rng = np.random.default_rng(n)
+        return np.unique(np.concatenate(([0, n - 1], rng.integers(0, n, _SAMPLE_ROWS - 2))))
+
+    def _rows_of(self, locator):
+        X = self.dof_locations
+        n = len(X)
+        if not self.strict_locators and n > _SAMPLE_ROWS:
+            try:
+                r = np.asarray(locator(X.T))
+                if r.shape == (n,) and r.dtype == np.bool_:
+                    rows = self._sample_rows(n)
+                    if all(bool(locator(X[k])) == bool(r[k]) for k in rows):
+                        return np.ascontiguousarray(r)
+            except Exception:
+                pass
+        return np.fromiter(map(locator, X), dtype=bool, count=n)       # the reference's path
+
+    def _values_of(self, get_value, rows):
+        '''float64 array of get_value(x) for the selected rows (odeSolver.py:183-187).'''
+        X = self.dof_locations[rows] if rows is not None else self.dof_locations
+        n = len(X)
+        if n == 0:
+            return np.empty(0)
+        if not self.strict_locators and n > _SAMPLE_ROWS:
+            try:
+                r = get_value(X.T)
+                if np.ndim(r) == 0:
+                    cand = np.full(n, float(r))
+                else:
+                    cand = np.asarray(r, dtype=np.float64)
+                if cand.shape == (n,):
+                    rows_s = self._sample_rows(n)
+                    ok = True
+                    for k in rows_s:
+                        v = float(get_value(X[k]))
+                        if not (v == cand[k] or (v != v and cand[k] != cand[k])):
+                            ok = False
+                            break
+                    if ok:
+                        return cand
+            except Exception:
+                pass
+        return np.fromiter((float(get_value(x)) for x in X), dtype=np.float64, count=n)
+
+    def _set_column(self, kind, col, src):
+        check(self._lib.kem_set_column(self._h, kind, col, src.ctypes.data, self.nodes), "kem_set_column")
+
+    def _get_column(self, kind, col, dst):
+        check(self._lib.kem_get_column(self._h, kind, col, dst.ctypes.data, self.nodes), "kem_get_column")
+
+    # --- Work horses (odeSolver.py:130-188)
+    def __set_ODE(self, what, which, u, locator=None):
+        '''ODE setting '''
+        kind, col = self._kind_col(what, which)
+        mask = self._mask(locator)
+        source = np.ascontiguousarray(np.asarray(u.x.array[:])[:self.nodes], dtype=np.float64)
+        if len(source) < self.nodes:
+            raise IndexError(f"u.x.array has {len(source)} entries, the membrane has {self.nodes} DOFs")
+        if self.nodes == 0:
+            return self.states
+        if mask is None:
+            self._set_column(kind, col, source)
+        elif mask.any():
+            m8 = np.ascontiguousarray(mask, dtype=np.uint8)
+            check(self._lib.kem_set_column_masked(self._h, kind, col, source.ctypes.data,
+                                                  m8.ctypes.data, self.nodes), "kem_set_column_masked")
+        return self.states
+
+    def __get_PDE(self, what, which, u, locator=None):
+        '''Update PDE potentials from the ODE solver'''
+        kind, col = self._kind_col(what, which)
+        mask = self._mask(locator)
+        if self.nodes == 0:
+            return u
+        dest = u.x.array
+        direct = (mask is None and isinstance(dest, np.ndarray) and dest.dtype == np.float64
+                  and dest.ndim == 1 and dest.flags.c_contiguous and dest.flags.writeable
+                  and len(dest) >= self.nodes)
+        if direct:
+            self._get_column(kind, col, dest)
+            return u
+        tmp = np.empty(self.nodes, dtype=np.float64)
+        self._get_column(kind, col, tmp)
+        destination = np.array(u.x.array[:], dtype=np.float64)
+        if mask is None:
+            destination[:self.nodes] = tmp
+        else:
+            destination[:self.nodes][mask] = tmp[mask]
+        u.x.array[:] = destination                                     # odeSolver.py:164
+        return u
+
+    def __set_ODE_values(self, what, value_dict, locator=None):
+        '''Batch setter'''
+        view = self.states if what == 'state' else self.parameters
+        mask = self._mask(locator)
+        n_sel = self.nodes if mask is None else int(mask.sum())
+        if self.verbose:
+            print(f'\t{self.prefix} Set {what} for {n_sel} ODES')
+        if n_sel == 0:
+            return view
+        rows = None if mask is None else np.nonzero(mask)[0]
+        for param in value_dict:
+            kind, col = self._kind_col(what, param)
+            vals = self._values_of(value_dict[param], rows)
+            uniform = bool(np.all(vals == vals[0])) or bool(np.all(vals != vals))
+            if mask is None:
+                if uniform:
+                    check(self._lib.kem_set_uniform(self._h, kind, col, float(vals[0])), "kem_set_uniform")
+                else:
+                    self._set_column(kind, col, np.ascontiguousarray(vals))
+            else:
+                m8 = np.ascontiguousarray(mask, dtype=np.uint8)
+                if uniform:
+                    check(self._lib.kem_set_value_masked(self._h, kind, col, float(vals[0]),
+                                                         m8.ctypes.data, self.nodes),
+                          "kem_set_value_masked")
+                else:
+                    full = np.zeros(self.nodes, dtype=np.float64)
+                    full[rows] = vals
+                    check(self._lib.kem_set_column_masked(self._h, kind, col, full.ctypes.data,
+                                                          m8.ctypes.data, self.nodes),
+                          "kem_set_column_masked")
+        return view
