@@ -133,6 +133,12 @@ int kem_set_block(kem_handle h, int block);
 /* number of kernels this handle has launched since creation */
 int kem_launch_count(kem_handle h, int64_t *n_out);
 
+/* CUDA-event stopwatch on the handle's launching streams: begin records an event on
+ * every device's stream, end records another, waits, and returns the largest elapsed
+ * time over the devices -- brackets K enqueue-only kem_step calls in the benchmark. */
+int kem_timer_begin(kem_handle h);
+int kem_timer_end(kem_handle h, double *ms_out);
+
 /* ---- pinned host memory for callers that want zero-staging transfers ---------- */
 int kem_host_alloc(void **ptr_out, size_t bytes);
 int kem_host_free(void *ptr);

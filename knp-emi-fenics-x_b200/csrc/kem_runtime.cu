@@ -133,6 +133,7 @@ struct Shard {
     int64_t begin = 0, n = 0;
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // kem_timer_begin / kem_timer_end
     std::vector<double *> ycol;   // ns per-DOF state columns
     std::vector<double *> pcol;   // np per-DOF parameter columns (allocation cached)
     double *d_uni = nullptr;      // np uniform parameter values
@@ -618,6 +619,8 @@ int kem_create(int model_id, int64_t n_dof, int n_dev, const int *dev_ids,
         CKB(cudaEventCreate(&s.ev_b));
         CKB(cudaEventCreate(&s.ev_c));
         CKB(cudaEventCreate(&s.ev_d));
+        CKB(cudaEventCreate(&s.ev_t0));
+        CKB(cudaEventCreate(&s.ev_t1));
         for (int r = 0; r < SMALL_RING; ++r) {
             CKB(cudaHostAlloc(&s.h_small[r], SMALL_BYTES, cudaHostAllocDefault));
             CKB(cudaEventCreateWithFlags(&s.small_ev[r], cudaEventDisableTiming));
@@ -674,7 +677,7 @@ int kem_destroy(kem_handle h)
         }
         for (auto *v : {&s.io_in, &s.io_k0, &s.io_k1, &s.io_out})
             for (cudaEvent_t e : *v) cudaEventDestroy(e);
-        for (cudaEvent_t e : {s.ev_a, s.ev_b, s.ev_c, s.ev_d}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {s.ev_a, s.ev_b, s.ev_c, s.ev_d, s.ev_t0, s.ev_t1}) if (e) cudaEventDestroy(e);
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.s_in) cudaStreamDestroy(s.s_in);
         if (s.s_out) cudaStreamDestroy(s.s_out);
@@ -1072,6 +1075,35 @@ int kem_sync(kem_handle h)
     if (rc) return rc;
     int flags = 0;
     return read_flags(h, &flags);
+}
+
+int kem_timer_begin(kem_handle h)
+{
+    ARG(h, "null handle");
+    for (Shard &s : h->shards) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaEventRecord(s.ev_t0, s.stream));
+    }
+    return KEM_OK;
+}
+
+int kem_timer_end(kem_handle h, double *ms_out)
+{
+    ARG(h && ms_out, "null argument");
+    for (Shard &s : h->shards) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaEventRecord(s.ev_t1, s.stream));
+    }
+    double worst = 0.0;
+    for (Shard &s : h->shards) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaEventSynchronize(s.ev_t1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s.ev_t0, s.ev_t1));
+        worst = std::max(worst, (double)ms);
+    }
+    *ms_out = worst;
+    return KEM_OK;
 }
 
 int kem_set_block(kem_handle h, int block)

@@ -77,6 +77,8 @@ SIGNATURES = {
                               C.c_int, C.POINTER(kem_io_column), C.c_int, C.POINTER(kem_io_column),
                               _IP, C.POINTER(kem_step_times)]),
     "kem_sync": (C.c_int, [_H]),
+    "kem_timer_begin": (C.c_int, [_H]),
+    "kem_timer_end": (C.c_int, [_H, _DP]),
     "kem_set_block": (C.c_int, [_H, C.c_int]),
     "kem_launch_count": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "kem_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),

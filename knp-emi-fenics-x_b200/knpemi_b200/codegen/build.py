@@ -121,6 +121,7 @@ def _build_key(em: EmittedModel, extra_flags=()) -> str:
     on any box the tree is copied to."""
     return _digest(em.source, _read(os.path.join(CSRC_DIR, "kem_kernel.cuh")),
                    _read(os.path.join(CSRC_DIR, "kem_model_api.h")),
+                   _read(os.path.join(CSRC_DIR, "kem_math.cuh")),
                    " ".join(NVCC_ARCH + NVCC_COMMON), " ".join(extra_flags))[:16]
 
 

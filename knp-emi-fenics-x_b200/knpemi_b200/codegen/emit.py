@@ -23,15 +23,20 @@ from dataclasses import dataclass
 from .ir import P, S, T, Dag, ModelSourceError
 from .parse import ParsedModel
 
-CODEGEN_VERSION = "3"
+CODEGEN_VERSION = "4"
 
 
 @dataclass
 class EmitOptions:
     default_block: int = 128
-    #: 0 = every operation as written; 1 = divisions by constants become
-    #: multiplications by the rounded reciprocal (<= 1 ulp per division)
-    fast_const_div: int = 0
+    #: "fast": exp and division through the branch-free <= 1 ulp routines of
+    #:         csrc/kem_math.cuh; x/const -> x*(1/const); const/x -> const*rcp(x);
+    #:         x/param -> x*rcp(param) with the reciprocal hoisted out of the loop.
+    #:         Every replaced operation stays within 1 ulp of the IEEE result.
+    #: "libm": every operation exactly as written, CUDA libm exp and IEEE division
+    #:         (the triage build: differs from the oracle only by FMA contraction
+    #:         and CUDA-vs-glibc libm).
+    math: str = "fast"
 
 
 @dataclass
@@ -68,6 +73,10 @@ class _Emitter:
             if not 0 <= c < np_:
                 raise ModelSourceError(f"parameters[{c}] outside the {np_} parameters of the model")
         self.out_cols = sorted(pm.out)
+        if opts.math not in ("fast", "libm"):
+            raise ValueError(f"unknown math mode {opts.math!r}")
+        self.fast = opts.math == "fast"
+        self.rcp_hoist = []      # parameter-only divisors of in-loop divisions
 
     # ------------------------------------------------------------------ naming
     def nm(self, nid: int) -> str:
@@ -125,11 +134,22 @@ class _Emitter:
         if op == "mul":
             return f"{a[0]} * {a[1]}"
         if op == "div":
-            if self.opts.fast_const_div and self.dag.is_const(n.args[1]):
-                return f"{a[0]} * {_lit(1.0 / self.dag.fvalue(n.args[1]))}"
+            if self.fast and ctx != "time":
+                num, den = n.args
+                if self.dag.is_const(den):
+                    return f"{a[0]} * {_lit(1.0 / self.dag.fvalue(den))}"
+                if ctx == "dyn" and den in self.rcp_hoist:
+                    return f"{a[0]} * q.r{den}"
+                if self.dag.is_const(num):
+                    if self.dag.fvalue(num) == 1.0:
+                        return f"kem::rcp({a[1]})"
+                    return f"{a[0]} * kem::rcp({a[1]})"
+                return f"kem::div({a[0]}, {a[1]})"
             return f"{a[0]} / {a[1]}"
         if op == "neg":
             return f"-{a[0]}"
+        if op == "exp" and self.fast and ctx != "time":
+            return f"kem::exp({a[0]})"
         if op in ("exp", "log", "sqrt"):
             return f"{op}({a[0]})"
         if op == "pow":
@@ -211,7 +231,14 @@ class _Emitter:
 
         for nid in order_all:
             if self.klass(nid) == "dyn":
-                for c in dag.nodes[nid].args:
+                node = dag.nodes[nid]
+                if self.fast and node.op == "div" and self.klass(node.args[1]) == "hoist":
+                    # x / <parameter-only>  ->  x * rcp, reciprocal taken once per PDE step
+                    if node.args[1] not in self.rcp_hoist:
+                        self.rcp_hoist.append(node.args[1])
+                    note(node.args[0])
+                    continue
+                for c in node.args:
                     note(c)
         for r in dy_roots + out_roots:
             note(r)
@@ -219,15 +246,17 @@ class _Emitter:
         time_front.sort()
         self.tslot = {nid: k for k, nid in enumerate(time_front)}
 
-        order_hoist = dag.reachable(hoist_front)
+        self.rcp_hoist.sort()
+        order_hoist = dag.reachable(hoist_front + self.rcp_hoist)
         order_time = dag.reachable(time_front)
 
         L = []
         w = L.append
         w(f"// GENERATED by knpemi_b200.codegen v{CODEGEN_VERSION} -- do not edit.")
         w(f"// model {name!r} from {pm.source_file}:{pm.lineno}")
-        w(f"// options: default_block={self.opts.default_block} fast_const_div={self.opts.fast_const_div}")
+        w(f"// options: default_block={self.opts.default_block} math={self.opts.math}")
         w('#include <math.h>')
+        w('#include "kem_math.cuh"')
         w('#include "kem_kernel.cuh"')
         w("")
         w("namespace {")
@@ -240,10 +269,11 @@ class _Emitter:
         w("")
         w("    // parameter-only values handed from hoist() to the sub-step loop")
         w("    struct H {")
-        if hoist_front:
-            for nid in hoist_front:
-                w(f"        double {self.nm(nid)};{self.comment(nid)}")
-        else:
+        for nid in hoist_front:
+            w(f"        double {self.nm(nid)};{self.comment(nid)}")
+        for nid in self.rcp_hoist:
+            w(f"        double r{nid};  // 1 / {self.dag.names.get(nid, self.nm(nid))}")
+        if not hoist_front and not self.rcp_hoist:
             w("        double unused;")
         w("    };")
         w("")
@@ -252,7 +282,9 @@ class _Emitter:
         L.extend(self.section(order_hoist, "hoist"))
         for nid in hoist_front:
             w(f"        q.{self.nm(nid)} = {self.operand(nid, 'hoist')};")
-        if not hoist_front:
+        for nid in self.rcp_hoist:
+            w(f"        q.r{nid} = kem::rcp({self.operand(nid, 'hoist')});")
+        if not hoist_front and not self.rcp_hoist:
             w("        q.unused = 0.0; (void)p;")
         w("    }")
         w("")

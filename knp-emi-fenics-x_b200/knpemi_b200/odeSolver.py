@@ -336,6 +336,16 @@ class MembraneModel:
         return self.last_step_times
 
     # ------------------------------------------------------------------ helpers
+    def timer_begin(self):
+        '''Record a CUDA event on every device's launching stream.'''
+        check(self._lib.kem_timer_begin(self._h), "kem_timer_begin")
+
+    def timer_end(self):
+        '''Milliseconds since :meth:`timer_begin` (CUDA events, max over the devices).'''
+        ms = C.c_double(0.0)
+        check(self._lib.kem_timer_end(self._h, C.byref(ms)), "kem_timer_end")
+        return ms.value
+
     def launch_count(self):
         n = C.c_int64(0)
         check(self._lib.kem_launch_count(self._h, C.byref(n)), "kem_launch_count")

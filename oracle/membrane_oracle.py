@@ -32,6 +32,9 @@ class OracleMembraneModel:
         self.nodes = nodes                                            # :38
         self.states = np.array([ode.init_state_values() for _ in range(nodes)])          # :41
         self.parameters = np.array([ode.init_parameter_values() for _ in range(nodes)])  # :42
+        if nodes == 0:     # np.array([]) is 1-D; keep the [N, ncols] shape for an empty membrane
+            self.states = np.zeros((0, len(ode.init_state_values())))
+            self.parameters = np.zeros((0, len(ode.init_parameter_values())))
         self.tag = tag
         self.ode = ode
         self.prefix = ode.__name__

@@ -1,0 +1,142 @@
+"""RHS -> CUDA generator: parser, DAG, dependency classes, emission (CPU only)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import MODEL_NAMES
+from knpemi_b200 import codegen
+from knpemi_b200.codegen import EmitOptions, ModelSourceError, generate_from_source, parse_model_source
+from knpemi_b200.codegen.interpret import evaluate
+from workloads import builtin
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _src(body, header="def rhs_numba(t, states, values, parameters):\n"):
+    return "import math\nimport numpy as np\n" + header + "".join("    " + ln + "\n" for ln in body)
+
+
+@pytest.mark.parametrize("name", MODEL_NAMES)
+def test_dag_evaluates_like_the_reference_cfunc(name):
+    """Parser + DAG semantics (folding, integer powers, association) against the golden
+    RHS vectors that came from the reference's numba cfuncs -- bit for bit."""
+    ode = builtin(name)
+    pm = parse_model_source(open(ode.__file__).read(), filename=ode.__file__)
+    g = np.load(os.path.join(GOLDEN, f"rhs_{name}.npz"))
+    for k in range(len(g["t"])):
+        dy, p_after = evaluate(pm, g["t"][k], g["y"][k], g["p"][k])
+        assert np.array_equal(np.array(dy), g["dy"][k], equal_nan=True)
+        assert np.array_equal(np.array(p_after), g["p_after"][k], equal_nan=True)
+
+
+@pytest.mark.parametrize("name", MODEL_NAMES)
+def test_emitted_model_facts(name):
+    ode = builtin(name)
+    em = codegen.generate(ode)
+    assert em.ns == len(ode.init_state_values()) and em.np == len(ode.init_parameter_values())
+    expected_out = {"hh_ideal": [15, 16, 17], "hh_tissue": [15, 16, 17], "glial_tissue": [5, 6, 7],
+                    "glial_bench": [9, 10, 11], "calibration": [], "hh_test": [8, 9, 10]}[name]
+    assert em.out_cols == expected_out
+    assert "kem_model_descriptor" not in em.source.split("KEM_DEFINE_MODEL")[0]
+    assert em.source.count("KEM_DEFINE_MODEL(") == 1
+    # time enters only through host-evaluated slots: no use of `t` in device code
+    device = em.source.split("static void tonly")[0]
+    assert "exp(" in device or name.startswith("glial") is False
+    # glial models have no time dependence at all
+    assert em.n_tslots == {"glial_tissue": 0, "glial_bench": 0, "calibration": 1}.get(name, 2)
+
+
+def test_generation_is_deterministic_and_path_independent(tmp_path):
+    ode = builtin("hh_tissue")
+    a = codegen.generate(ode)
+    b = codegen.generate(ode)
+    assert a.source == b.source and a.source_hash == b.source_hash
+    # same source under another directory gives the same translation unit
+    src = open(ode.__file__).read()
+    c = generate_from_source(src, "hh_tissue", a.ns, a.np, filename=os.path.basename(ode.__file__))
+    assert c.source == a.source
+
+
+def test_math_modes_emit_different_code():
+    ode = builtin("hh_ideal")
+    fast = codegen.generate(ode, EmitOptions(math="fast")).source
+    libm = codegen.generate(ode, EmitOptions(math="libm")).source
+    assert "kem::exp(" in fast and "kem::exp(" not in libm
+    assert "kem::div(" in fast and " / " in libm
+    with pytest.raises(ValueError):
+        codegen.generate(ode, EmitOptions(math="wrong"))
+
+
+def test_dependency_classes_and_hoisting():
+    body = [
+        "a = parameters[0] * parameters[1]",              # parameter-only -> hoisted
+        "g = np.exp(-np.mod(t, 2.0)) * (t < 5)",           # time-only      -> host slot
+        "c = math.exp(1.0) + 2",                          # constant       -> folded
+        "values[0] = a * states[0] + g * parameters[2] + c",
+        "parameters[3] = a - states[0]",
+    ]
+    em = generate_from_source(_src(body), "toy", 1, 4)
+    assert em.out_cols == [3] and em.used_cols == [0, 1, 2]
+    assert em.n_tslots == 1
+    hoist = em.source.split("void hoist")[1].split("void deriv")[0]
+    deriv = em.source.split("void deriv")[1].split("void outputs")[0]
+    assert "p[0] * p[1]" in hoist and "p[0]" not in deriv
+    assert "exp" not in deriv                               # both exps live elsewhere
+    import math
+    assert float.hex(math.exp(1.0) + 2) in deriv            # folded constant, exact literal
+    tonly = em.source.split("static void tonly")[1]
+    assert "kem_npmod_host(t" in tonly and "exp(" in tonly
+
+
+def test_integer_power_lowering_matches_numba_order():
+    pm = parse_model_source(_src(["values[0] = states[0]**3 + math.pow(states[0], 4) + states[0]**1.5"]))
+    x = 1.2345678901234567
+    dy, _ = evaluate(pm, 0.0, [x], [])
+    x2 = x * x
+    import math
+    assert dy[0] == (x * x2 + x2 * x2) + math.pow(x, 1.5)
+    em = generate_from_source(_src(["values[0] = states[0]**3"]), "p3", 1, 0)
+    assert "y[0] * y[0]" in em.source and "pow(" not in em.source.split("tonly")[0]
+
+
+def test_docstrings_and_comment_blocks_are_skipped():
+    body = ['"""docstring"""', "x = states[0]", '"""', "old = code(here)", '"""', "values[0] = -x"]
+    em = generate_from_source(_src(body), "doc", 1, 0)
+    assert em.ns == 1
+
+
+@pytest.mark.parametrize("body,msg", [
+    (["for i in range(3):", "    values[0] = 1.0"], "only simple assignments"),
+    (["values[0] = math.sin(states[0])"], "unsupported call"),
+    (["values[0] = states[i]"], "integer literals"),
+    (["values[0] = undefined_name"], "not defined"),
+    (["values[0] = states[0] if t > 0 else 1.0"], "unsupported expression"),
+    (["parameters[0] = 1.0", "values[0] = parameters[0]"], "read after"),
+    (["x = 1.0"], "assigns no values"),
+    (["values[1] = 1.0"], "outside the 1 states"),
+    (["values[0] = 1.0/0.0"], "constant expression"),
+])
+def test_unsupported_constructs_are_rejected(body, msg):
+    with pytest.raises(ModelSourceError, match=msg):
+        generate_from_source(_src(body), "bad", 1, 1)
+
+
+def test_missing_rhs_function():
+    with pytest.raises(ModelSourceError, match="no top-level function"):
+        parse_model_source("def other(t, y, dy, p):\n    dy[0] = 0.0\n")
+
+
+def test_model_without_source_file_is_refused():
+    class Fake:
+        __name__ = "fake"
+
+        @staticmethod
+        def init_state_values():
+            return np.zeros(1)
+
+        @staticmethod
+        def init_parameter_values():
+            return np.zeros(1)
+    with pytest.raises(ModelSourceError, match="__file__"):
+        codegen.generate(Fake)

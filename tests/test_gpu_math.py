@@ -1,0 +1,77 @@
+"""Device build of kem_math.cuh against CUDA's own libm / IEEE division, through a model
+whose 'dynamics' are just exp and divisions of the state (so the comparison runs through
+the real generator + kernel + C ABI path in both math modes)."""
+import importlib.util
+import textwrap
+
+import numpy as np
+import pytest
+
+from ducks_for_tests import Func, Space
+
+pytestmark = pytest.mark.gpu
+
+SRC = textwrap.dedent('''
+    import math
+    import numpy as np
+    def init_state_values(**values):
+        return np.array([0.0, 1.0], dtype=np.float64)
+    def init_parameter_values(**values):
+        return np.array([0.0, 0.0, 0.0, 0.0], dtype=np.float64)
+    def state_indices(*names):
+        d = {"V": 0, "w": 1}
+        r = [d[n] for n in names]
+        return r if len(r) > 1 else r[0]
+    def parameter_indices(*names):
+        d = {"o_exp": 0, "o_div": 1, "o_rcp": 2, "o_sing": 3}
+        r = [d[n] for n in names]
+        return r if len(r) > 1 else r[0]
+    def rhs_numba(t, states, values, parameters):
+        parameters[0] = math.exp(states[0])
+        parameters[1] = states[0] / states[1]
+        parameters[2] = 1.0 / states[1]
+        parameters[3] = states[0] / (math.exp(states[0]) - 1.0)
+        values[0] = 0.0 * states[0]
+        values[1] = 0.0 * states[1]
+''')
+
+
+def _outputs(tmp_path, math, x, w):
+    from knpemi_b200.codegen import EmitOptions
+    from knpemi_b200.odeSolver import MembraneModel
+    path = tmp_path / "mm_math_probe.py"
+    path.write_text(SRC)
+    spec = importlib.util.spec_from_file_location("mm_math_probe", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    m = MembraneModel(mod, None, 1, Space(np.zeros((len(x), 3))), verbose=False, devices=[0],
+                      emit_options=EmitOptions(math=math), n_sub=1)
+    m.set_state('V', Func(x))
+    m.set_state('w', Func(w))
+    m.step_lsoda(1.0, None)
+    out = np.asarray(m.parameters)
+    m.close()
+    return out
+
+
+def test_device_exp_div_rcp_within_one_ulp_of_libm(built, tmp_path):
+    rng = np.random.default_rng(0)
+    n = 400_000
+    x = np.concatenate([rng.uniform(-700, 700, n // 2), rng.uniform(-30, 30, n // 4),
+                        rng.uniform(-1e-3, 1e-3, n // 4)])
+    w = np.ldexp(rng.uniform(1, 2, n), rng.integers(-200, 200, n)) * rng.choice([-1.0, 1.0], n)
+    fast = _outputs(tmp_path, "fast", x, w)
+    libm = _outputs(tmp_path, "libm", x, w)
+    with np.errstate(over="ignore"):
+        want_exp = np.exp(x.astype(np.longdouble))
+        want_div = x.astype(np.longdouble) / w.astype(np.longdouble)
+        want_rcp = 1.0 / w.astype(np.longdouble)
+    for col, want in ((0, want_exp), (1, want_div), (2, want_rcp)):
+        ulp = np.spacing(np.abs(want.astype(np.float64)))
+        err_fast = np.abs(fast[:, col].astype(np.longdouble) - want) / ulp
+        err_libm = np.abs(libm[:, col].astype(np.longdouble) - want) / ulp
+        assert err_fast.max() <= 1.0, (col, float(err_fast.max()))
+        assert err_libm.max() <= 1.0, (col, float(err_libm.max()))
+    # division and reciprocal are correctly rounded in both builds -> identical bits
+    assert np.array_equal(fast[:, 1], libm[:, 1])
+    assert np.array_equal(fast[:, 2], libm[:, 2])
