@@ -9,14 +9,16 @@
 // independent exps of a Hodgkin-Huxley right-hand side into separate basic
 // blocks (no interleaving -> "wait" stalls), and the 59 KB loop body misses the
 // instruction cache ("no_instructions" stalls).  The versions below are
-// straight-line: 16 FP64-pipe instructions per exp, 8 (+1 MUFU) per division.
+// straight-line: 16 FP64-pipe instructions per exp, 6 (+1 MUFU) per division,
+// 3 (+1 MUFU) per reciprocal.
 //
 // Accuracy (tests/test_kem_math.py, host build of this same header against
-// long-double libm): exp <= 1 ulp on [-708, 709]; div, rcp <= 1 ulp.
+// long-double libm; tests/test_gpu_math.py on the device): exp < 1 ulp on
+// [-708, 709]; rcp, div correctly rounded (0.5 ulp) in their domain.
 // Domain notes, all outside anything a finite membrane state produces:
-//   * exp saturates instead of overflowing: x > 709.78 gives ~2^1023..2^1024
-//     (finite), x < -708.4 gives ~2^-1022; NaN propagates.
-//   * rcp/div assume a normal, non-zero divisor (|b| in [2^-1020, 2^1020]);
+//   * exp flushes to 0 below x = -708.4 (no denormal results), returns +inf above
+//     709.09 (libm: above 709.78); NaN propagates; exp(+-inf) is NaN.
+//   * rcp/div assume a normal, non-zero divisor and quotient (|b| in [2^-1020, 2^1020]);
 //     b = 0 gives NaN instead of +-inf.
 #pragma once
 #include <math.h>
@@ -54,9 +56,10 @@ KEM_HD uint64_t double_to_bits(double d)
 }
 
 // ~20-bit reciprocal seed.  Device: MUFU.RCP64H (rcp.approx.ftz.f64: ignores the
-// low 32 mantissa bits of the input, returns zero low word).  Host: the same
+// low 32 mantissa bits of the input, returns a zero low word; measured on B200:
+// max |1 - b r| = 2^-19.94, tools/probes/probe_rcp_seed.cu).  Host: the same
 // truncations around an exact division, so the host build exercises the same
-// Newton iterations from an equally coarse start.
+// refinement from an equally coarse start.
 KEM_HD double rcp_seed(double b)
 {
 #if defined(__CUDA_ARCH__)
@@ -66,19 +69,18 @@ KEM_HD double rcp_seed(double b)
 #else
     const double bt = bits_to_double(double_to_bits(b) & 0xFFFFFFFF00000000ull);
     const double r = 1.0 / bt;
-    return bits_to_double(double_to_bits(r) & 0xFFFFFFFFFFF00000ull & 0xFFFFFFFF00000000ull);
+    return bits_to_double(double_to_bits(r) & 0xFFFFFFFF00000000ull);
 #endif
 }
 
-// 1/b : two Newton steps from the seed (2^-20 -> 2^-40 -> rounding level)
+// 1/b : one third-order step from the seed, r1 = r0 (1 + e + e^2), e = 1 - b r0.
+// |e| <= 2^-19.9 leaves a truncation error of e^3 <= 2^-59.8 before the final rounding.
 KEM_HD double rcp(double b)
 {
-    double r = rcp_seed(b);
-    double e = fma(-b, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-b, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double r = rcp_seed(b);
+    const double e = fma(-b, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 }
 
 // a/b : reciprocal, then one residual correction of the quotient
@@ -90,34 +92,63 @@ KEM_HD double div(double a, double b)
     return fma(rem, r, q);
 }
 
+// Constants of exp() in one table.  On the device it lives in constant memory so
+// that ptxas loads it into uniform registers once (LDCU.128, two doubles per
+// instruction) instead of re-materialising every 64-bit literal with a UMOV pair
+// inside the sub-step loop (what the first fast build did: 34 UMOV per stage).
+#define KEM_EXP_TABLE                                                                   \
+    {0x1.71547652b82fep+0,  /* [0]  1/ln2 */                                            \
+     0x1.8p+52 + 1023.0,    /* [1]  1.5*2^52 + bias: low word of the sum = k + 1023 */  \
+     -0x1.62e42fefa39efp-1, /* [2]  -ln2 (high part) */                                 \
+     -0x1.abc9e3b39803fp-56,/* [3]  -ln2 (low part)  */                                 \
+     0x1.af38a9b0ec855p-26, /* [4]  c11 */                                              \
+     0x1.289185613a3d6p-22, /* [5]  c10 */                                              \
+     0x1.71de0dae63bb3p-19, /* [6]  c9  */                                              \
+     0x1.a019b90d2ae7ap-16, /* [7]  c8  */                                              \
+     0x1.a01a01a7c41d5p-13, /* [8]  c7  */                                              \
+     0x1.6c16c1788bd90p-10, /* [9]  c6  */                                              \
+     0x1.11111111109b3p-7,  /* [10] c5  */                                              \
+     0x1.5555555553d63p-5,  /* [11] c4  */                                              \
+     0x1.5555555555556p-3,  /* [12] c3  */                                              \
+     0x1.0000000000001p-1}  /* [13] c2  */
+
+#if defined(__CUDACC__)
+__constant__ double KEM_EXP_C_DEV[14] = KEM_EXP_TABLE;
+#endif
+static const double KEM_EXP_C_HOST[14] = KEM_EXP_TABLE;
+
+#if defined(__CUDA_ARCH__)
+#define KEM_EXP_C KEM_EXP_C_DEV
+#else
+#define KEM_EXP_C KEM_EXP_C_HOST
+#endif
+
 // exp(x) = 2^k * p(r),  k = rint(x/ln2),  r = x - k ln2 in [-ln2/2, ln2/2],
 // p = degree-11 polynomial (Chebyshev-node fit of (e^r-1-r)/r^2, c0 = c1 = 1;
 // max relative error 1.6e-17 before rounding, tools/fit_exp_poly.py).
+// 2^k is assembled in the integer pipe from the low word of the magic-number sum,
+// clamped to the exponent field: k < -1022 gives 0, k > 1023 gives +inf.
 KEM_HD double exp(double x)
 {
-    const double L2E = 0x1.71547652b82fep+0;      // 1/ln2
-    const double LN2_HI = 0x1.62e42fefa39efp-1;
-    const double LN2_LO = 0x1.abc9e3b39803fp-56;
-    const double MAGIC = 0x1.8p+52;               // 1.5 * 2^52: low word of the sum holds k
-    const double t = fma(x, L2E, MAGIC);
-    const double kd = t - MAGIC;
-    double r = fma(kd, -LN2_HI, x);
-    r = fma(kd, -LN2_LO, r);
-    double p = 0x1.af38a9b0ec855p-26;
-    p = fma(p, r, 0x1.289185613a3d6p-22);
-    p = fma(p, r, 0x1.71de0dae63bb3p-19);
-    p = fma(p, r, 0x1.a019b90d2ae7ap-16);
-    p = fma(p, r, 0x1.a01a01a7c41d5p-13);
-    p = fma(p, r, 0x1.6c16c1788bd90p-10);
-    p = fma(p, r, 0x1.11111111109b3p-7);
-    p = fma(p, r, 0x1.5555555553d63p-5);
-    p = fma(p, r, 0x1.5555555555556p-3);
-    p = fma(p, r, 0x1.0000000000001p-1);
+    const double t = fma(x, KEM_EXP_C[0], KEM_EXP_C[1]);
+    const double kd = t - KEM_EXP_C[1];
+    double r = fma(kd, KEM_EXP_C[2], x);
+    r = fma(kd, KEM_EXP_C[3], r);
+    double p = KEM_EXP_C[4];
+    p = fma(p, r, KEM_EXP_C[5]);
+    p = fma(p, r, KEM_EXP_C[6]);
+    p = fma(p, r, KEM_EXP_C[7]);
+    p = fma(p, r, KEM_EXP_C[8]);
+    p = fma(p, r, KEM_EXP_C[9]);
+    p = fma(p, r, KEM_EXP_C[10]);
+    p = fma(p, r, KEM_EXP_C[11]);
+    p = fma(p, r, KEM_EXP_C[12]);
+    p = fma(p, r, KEM_EXP_C[13]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    int k = (int)(uint32_t)(double_to_bits(t) & 0xFFFFFFFFull);
-    k = k < -1022 ? -1022 : (k > 1023 ? 1023 : k);
-    const double scale = bits_to_double((uint64_t)(uint32_t)(k + 1023) << 52);
+    int u = (int)(uint32_t)(double_to_bits(t) & 0xFFFFFFFFull);   // k + 1023
+    u = u < 0 ? 0 : (u > 2047 ? 2047 : u);
+    const double scale = bits_to_double((uint64_t)(uint32_t)u << 52);
     return p * scale;
 }
 

@@ -23,7 +23,7 @@ from dataclasses import dataclass
 from .ir import P, S, T, Dag, ModelSourceError
 from .parse import ParsedModel
 
-CODEGEN_VERSION = "4"
+CODEGEN_VERSION = "5"
 
 
 @dataclass
@@ -77,6 +77,25 @@ class _Emitter:
             raise ValueError(f"unknown math mode {opts.math!r}")
         self.fast = opts.math == "fast"
         self.rcp_hoist = []      # parameter-only divisors of in-loop divisions
+        self.const_table = []    # device literals that are not 32-bit immediates
+
+    def dev_lit(self, v: float) -> str:
+        """Device-side constant.  A double whose low mantissa word is zero (1.0, 25.0,
+        4000.0, ...) is a free 32-bit immediate of DFMA/DADD/DMUL; every other literal
+        would be rebuilt with two UMOV per use inside the sub-step loop, so those go to
+        a __constant__ table that ptxas loads into uniform registers once."""
+        import struct
+        v = float(v)
+        if math.isnan(v) or math.isinf(v):
+            raise ModelSourceError("non-finite constant in model expression")
+        if struct.unpack("<Q", struct.pack("<d", v))[0] & 0xFFFFFFFF == 0:
+            return _lit(v)
+        key = v.hex()
+        for k, (kk, _) in enumerate(self.const_table):
+            if kk == key:
+                return f"KC[{k}]"
+        self.const_table.append((key, v))
+        return f"KC[{len(self.const_table) - 1}]"
 
     # ------------------------------------------------------------------ naming
     def nm(self, nid: int) -> str:
@@ -100,10 +119,8 @@ class _Emitter:
     def operand(self, nid: int, ctx: str) -> str:
         """C++ text for reading node ``nid`` from code section ``ctx``."""
         n = self.dag.nodes[nid]
-        if n.op == "const":
-            return _lit(n.val)
-        if n.op == "iconst":
-            return _lit(float(n.val))
+        if n.op in ("const", "iconst"):
+            return _lit(float(n.val)) if ctx == "time" else self.dev_lit(float(n.val))
         k = self.klass(nid)
         if ctx == "dyn":
             if n.op == "state":
@@ -137,7 +154,7 @@ class _Emitter:
             if self.fast and ctx != "time":
                 num, den = n.args
                 if self.dag.is_const(den):
-                    return f"{a[0]} * {_lit(1.0 / self.dag.fvalue(den))}"
+                    return f"{a[0]} * {self.dev_lit(1.0 / self.dag.fvalue(den))}"
                 if ctx == "dyn" and den in self.rcp_hoist:
                     return f"{a[0]} * q.r{den}"
                 if self.dag.is_const(num):
@@ -260,6 +277,7 @@ class _Emitter:
         w('#include "kem_kernel.cuh"')
         w("")
         w("namespace {")
+        w("@@CONST_TABLE@@")
         w("struct Model {")
         w(f"    static constexpr int NS = {self.ns}, NP = {self.np}, NOUT = {len(self.out_cols)}, "
           f"NT = {len(time_front)};")
@@ -323,7 +341,13 @@ class _Emitter:
         w(f"const int USED_COLS[] = {{{uc}}};")
         w("}  // namespace")
         w("")
-        body = "\n".join(L)
+        if self.const_table:
+            rows = ",\n".join(f"    {_lit(v)}  /* [{k}] {v!r} */" for k, (_, v) in enumerate(self.const_table))
+            table = ("// literals that are not 32-bit immediates (see _Emitter.dev_lit)\n"
+                     f"__constant__ double KC[{len(self.const_table)}] = {{\n{rows}}};\n")
+        else:
+            table = ""
+        body = "\n".join(L).replace("@@CONST_TABLE@@", table)
         h = hashlib.sha256(body.encode()).hexdigest()[:16]
         body += (f'\nKEM_DEFINE_MODEL(Model, "{name}", "{h}", OUT_COLS, USED_COLS, {len(used_cols)})\n')
 

@@ -84,7 +84,8 @@ def test_dependency_classes_and_hoisting():
     assert "p[0] * p[1]" in hoist and "p[0]" not in deriv
     assert "exp" not in deriv                               # both exps live elsewhere
     import math
-    assert float.hex(math.exp(1.0) + 2) in deriv            # folded constant, exact literal
+    assert float.hex(math.exp(1.0) + 2) in em.source        # folded constant, exact literal ...
+    assert "KC[" in deriv                                   # ... read from the constant table
     tonly = em.source.split("static void tonly")[1]
     assert "kem_npmod_host(t" in tonly and "exp(" in tonly
 
