@@ -68,10 +68,10 @@ def test_kernel_matches_oracle(built, name):
 @pytest.mark.parametrize("name", ("hh_ideal", "calibration", "glial_bench"))
 def test_libm_build_matches_oracle_tightly(built, name):
     """The triage build (CUDA libm exp, IEEE division) differs from the oracle only by
-    FMA contraction and libm last-bit differences: states three orders tighter than RTOL
+    FMA contraction and libm last-bit differences: states two orders tighter than RTOL
     (the currents carry the cancellation noise described in `scales`)."""
     got_S, got_P, S, P = run_pair(name, 5000, 10, math="libm")
-    assert rel_err(got_S, S, scales(S)) < 1e-13
+    assert rel_err(got_S, S, scales(S)) < 1e-12
     assert rel_err(got_P, P, scales(P)) < 5e-11
 
 
