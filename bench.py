@@ -39,6 +39,7 @@ for _p in (os.path.join(ROOT, "tests"), os.path.join(ROOT, "knp-emi-fenics-x_b20
 
 import numpy as np  # noqa: E402
 
+_emit = print
 METRIC = "membrane DOF-steps/sec (fp64)"
 UNIT = "DOF-steps/s"
 N_SUB = 25
@@ -138,7 +139,8 @@ class Dist:
             if backend == "nccl":
                 torch.cuda.set_device(self.local_rank)
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
+            kw = {"device_id": torch.device("cuda", self.local_rank)} if backend == "nccl" else {}
+            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world, **kw)
             self.backend = backend
 
     def barrier(self):
@@ -264,7 +266,7 @@ def run_reference(args, dist: Dist):
         "note": "reference = CPU stepping; timed: oracle port of odeSolver.py:107-122 with the reference's "
                 "RHS, OpenMP over rows, all host threads (numbalsoda/dolfinx not installable offline)",
     }
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------ GPU arm
@@ -422,7 +424,7 @@ def run_gpu(args, dist: Dist):
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        _emit(json.dumps(line))
 
 
 def main():
@@ -437,6 +439,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # exactly one line on stdout: library chatter (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda line: (real_stdout.write(line + "\n"), real_stdout.flush())     # noqa: E731
     dist = Dist()
     if dist.world != args.gpus and dist.world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={dist.world}")
