@@ -7,6 +7,7 @@
 // fallback: every path below ends in a CUDA call on the handle's devices.
 #include "../../include/knpemi_b200.h"
 #include "kem_model_api.h"
+#include "kem_copy_pool.h"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -48,85 +49,6 @@ int fail(int code, const std::string &msg)
     do {                                                                                 \
         if (!(cond)) return fail(KEM_E_ARG, std::string(__func__) + ": " + (msg));       \
     } while (0)
-
-// ------------------------------------------------------------------ host copy pool
-// Pageable caller buffers (what `u.x.array` of a dolfinx Function is) have to pass through
-// pinned staging memory; one core moves ~10 GB/s, a PCIe 5 x16 link ~50 GB/s, so the
-// staging copies are spread over a few persistent worker threads.
-class CopyPool {
-public:
-    static CopyPool &get()
-    {
-        static CopyPool pool;
-        return pool;
-    }
-
-    void copy(void *dst, const void *src, size_t bytes)
-    {
-        const size_t min_part = 1u << 20;
-        int parts = (int)std::min<size_t>(workers_.size() + 1, (bytes + min_part - 1) / min_part);
-        if (parts <= 1) {
-            memcpy(dst, src, bytes);
-            return;
-        }
-        std::unique_lock<std::mutex> call_lock(call_mu_);      // one parallel copy at a time
-        const size_t per = ((bytes + parts - 1) / parts + 63) / 64 * 64;
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            dst_ = (char *)dst;
-            src_ = (const char *)src;
-            bytes_ = bytes;
-            per_ = per;
-            next_ = 1;
-            parts_ = parts;
-            pending_ = parts - 1;
-            ++generation_;
-        }
-        cv_.notify_all();
-        memcpy(dst, src, std::min(per, bytes));                 // part 0 on the calling thread
-        std::unique_lock<std::mutex> lk(mu_);
-        done_cv_.wait(lk, [&] { return pending_ == 0; });
-    }
-
-private:
-    CopyPool()
-    {
-        unsigned hw = std::thread::hardware_concurrency();
-        int n = (int)std::min<unsigned>(7u, hw > 2 ? hw / 2 - 1 : 0);
-        if (const char *e = getenv("KNPEMI_COPY_THREADS")) n = std::max(0, atoi(e) - 1);
-        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
-        for (auto &t : workers_) t.detach();
-    }
-
-    void run()
-    {
-        unsigned long seen = 0;
-        for (;;) {
-            int part;
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return generation_ != seen && next_ < parts_; });
-                part = next_++;
-                if (next_ >= parts_) seen = generation_;
-            }
-            const size_t off = (size_t)part * per_;
-            if (off < bytes_) memcpy(dst_ + off, src_ + off, std::min(per_, bytes_ - off));
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                if (--pending_ == 0) done_cv_.notify_one();
-            }
-        }
-    }
-
-    std::vector<std::thread> workers_;
-    std::mutex mu_, call_mu_;
-    std::condition_variable cv_, done_cv_;
-    char *dst_ = nullptr;
-    const char *src_ = nullptr;
-    size_t bytes_ = 0, per_ = 0;
-    int next_ = 0, parts_ = 0, pending_ = 0;
-    unsigned long generation_ = 0;
-};
 
 // ------------------------------------------------------------------ utility kernels
 __global__ void k_fill(double *__restrict__ dst, long long n, double v)

@@ -55,7 +55,8 @@ def _run(cmd, what):
 def build_runtime(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/kem_runtime.cu -> lib/libknpemi_b200.so (sm_100a)."""
     src = os.path.join(CSRC_DIR, "kem_runtime.cu")
-    deps = [src, os.path.join(CSRC_DIR, "kem_model_api.h"), os.path.join(INCLUDE_DIR, "knpemi_b200.h")]
+    deps = [src, os.path.join(CSRC_DIR, "kem_model_api.h"), os.path.join(CSRC_DIR, "kem_copy_pool.h"),
+            os.path.join(INCLUDE_DIR, "knpemi_b200.h")]
     key = _digest(*[_read(d) for d in deps], " ".join(NVCC_ARCH + NVCC_COMMON))
     stamp = RUNTIME_LIB + ".key"
     if not force and os.path.exists(RUNTIME_LIB) and os.path.exists(stamp) \
