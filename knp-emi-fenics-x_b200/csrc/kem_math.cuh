@@ -10,7 +10,7 @@
 // blocks (no interleaving -> "wait" stalls), and the 59 KB loop body misses the
 // instruction cache ("no_instructions" stalls).  The versions below are
 // straight-line: 16 FP64-pipe instructions per exp, 6 (+1 MUFU) per division,
-// 3 (+1 MUFU) per reciprocal.
+// 3 (+1 MUFU) per reciprocal, 7 (+1 MUFU) per sqrt, ~27 per log.
 //
 // Accuracy (tests/test_kem_math.py, host build of this same header against
 // long-double libm; tests/test_gpu_math.py on the device): exp < 1 ulp on
@@ -150,6 +150,95 @@ KEM_HD double exp(double x)
     u = u < 0 ? 0 : (u > 2047 ? 2047 : u);
     const double scale = bits_to_double((uint64_t)(uint32_t)u << 52);
     return p * scale;
+}
+
+// ~20-bit reciprocal-square-root seed (device: MUFU.RSQ64H; host: truncated 1/sqrt).
+KEM_HD double rsqrt_seed(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+#else
+    const double xt = bits_to_double(double_to_bits(x) & 0xFFFFFFFF00000000ull);
+    const double r = 1.0 / ::sqrt(xt);
+    return bits_to_double(double_to_bits(r) & 0xFFFFFFFF00000000ull);
+#endif
+}
+
+// sqrt(x), x > 0 normal: coupled Newton step on (g ~ sqrt x, h ~ 1/(2 sqrt x)) from the
+// seed (2^-20 -> 2^-40), then one residual correction g += (x - g^2) h (-> rounding level).
+// 7 FP64 instructions + 1 MUFU.  sqrt(0) is NaN here (0 * inf); negative x gives NaN.
+KEM_HD double sqrt(double x)
+{
+    const double y = rsqrt_seed(x);
+    double g = x * y;
+    double h = 0.5 * y;
+    const double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double d = fma(-g, g, x);
+    return fma(d, h, g);
+}
+
+// x^1.5 = x sqrt(x): two roundings, <= 1 ulp (CUDA's pow is specified to 2 ulp).
+KEM_HD double pow15(double x) { return x * kem::sqrt(x); }
+
+#define KEM_LOG_TABLE                                                                   \
+    {0x1.5555555555558p-1, /* Lg1 */ 0x1.99999999949a8p-2, /* Lg2 */                    \
+     0x1.2492492ef4288p-2, /* Lg3 */ 0x1.c71c619eb4eadp-3, /* Lg4 */                    \
+     0x1.746310bc043a5p-3, /* Lg5 */ 0x1.39f28b0407abap-3, /* Lg6 */                    \
+     0x1.2be91695763e8p-3, /* Lg7 */                                                    \
+     0x1.62e42fee00000p-1, /* ln2 high: low 21 mantissa bits zero, k*ln2_hi exact */    \
+     0x1.a39ef35793c76p-33 /* ln2 low */}
+
+#if defined(__CUDACC__)
+__constant__ double KEM_LOG_C_DEV[9] = KEM_LOG_TABLE;
+#endif
+static const double KEM_LOG_C_HOST[9] = KEM_LOG_TABLE;
+#if defined(__CUDA_ARCH__)
+#define KEM_LOG_C KEM_LOG_C_DEV
+#else
+#define KEM_LOG_C KEM_LOG_C_HOST
+#endif
+
+// log(x), x > 0 normal.  x = 2^k m, m in [sqrt(1/2), sqrt(2)); f = m - 1; s = f/(2+f);
+// log(1+f) = f - hfsq + s (hfsq + R(s^2)), hfsq = f^2/2 (the classic fdlibm arrangement;
+// coefficients from tools/fit_log_poly.py).  Straight-line; x <= 0, inf, NaN are patched
+// at the end with selects: log(0) = -inf, log(x<0) = NaN, log(inf) = inf.
+// Denormal x is treated as 0 (-inf).
+KEM_HD double log(double x)
+{
+    const uint64_t bx = double_to_bits(x);
+    int hx = (int)(uint32_t)(bx >> 32);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int i = (hx + 0x95f64) & 0x100000;          // mantissa above sqrt(2): halve it
+    k += i >> 20;
+    const uint64_t bm = ((uint64_t)(uint32_t)(hx | (i ^ 0x3ff00000)) << 32) | (bx & 0xFFFFFFFFull);
+    const double f = bits_to_double(bm) - 1.0;
+    const double dk = (double)k;
+    const double s = f * kem::rcp(2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    double t1 = fma(w, KEM_LOG_C[5], KEM_LOG_C[3]);
+    t1 = fma(w, t1, KEM_LOG_C[1]);
+    t1 = w * t1;
+    double t2 = fma(w, KEM_LOG_C[6], KEM_LOG_C[4]);
+    t2 = fma(w, t2, KEM_LOG_C[2]);
+    t2 = fma(w, t2, KEM_LOG_C[0]);
+    const double R = fma(z, t2, t1);
+    const double hfsq = 0.5 * f * f;
+    // dk*ln2_hi - ((hfsq - (s*(hfsq+R) + dk*ln2_lo)) - f)
+    const double a = fma(s, hfsq + R, dk * KEM_LOG_C[8]);
+    double res = fma(dk, KEM_LOG_C[7], -((hfsq - a) - f));
+    // special operands, decided on the high word in the integer pipe:
+    // x < 2^-1022 (zero, denormal, any negative) and exponent field all ones (inf, NaN)
+    const int hx0 = (int)(uint32_t)(bx >> 32);
+    const double low = bits_to_double(hx0 < 0 ? 0x7FF8000000000000ull : 0xFFF0000000000000ull);
+    res = (hx0 < 0x00100000) ? low : res;              // -> NaN for negatives, -inf for 0
+    res = (hx0 >= 0x7ff00000) ? x : res;               // +inf -> +inf, NaN -> NaN
+    return res;
 }
 
 }  // namespace kem

@@ -132,6 +132,7 @@ constexpr size_t SMALL_BYTES = 64 * 1024;
 constexpr int N_STAGE = 3;
 constexpr size_t STAGE_BYTES = 8u << 20;
 constexpr int IO_MAX_CHUNKS = 64;
+constexpr int IO_TARGET_CHUNKS = 16;   // measured best of 8/16/32/64 at 1e7 DOFs (profiles/r1_bench.md)
 
 struct Shard {
     int dev = 0;
@@ -332,6 +333,19 @@ void build_ttab(const KemModelDesc *m, double t0, double dt, int n_sub, std::vec
     const double tc = t0 + ((double)(n_sub - 1) + 1.0) * hstep;
     m->tonly(tc, &tab[(size_t)(2 * n_sub) * nt]);
     m->tonly(t0 + dt, &tab[(size_t)(2 * n_sub + 1) * nt]);
+}
+
+// DOF chunks of one pipelined exchange (kem_step_io): enough chunks that the pipeline
+// fill/drain (one chunk of kernel + D2H) is a few percent of the exchange, chunks large
+// enough (>= 128k DOFs) that each launch still fills the GPU for several waves.
+int io_chunks(int64_t n, int64_t *chunk_out)
+{
+    int target = IO_TARGET_CHUNKS;
+    if (const char *e = getenv("KNPEMI_IO_CHUNKS")) target = std::max(1, std::min(atoi(e), IO_MAX_CHUNKS));
+    int64_t chunk = std::max<int64_t>((n + target - 1) / target, 1 << 17);
+    chunk = (chunk + 1023) / 1024 * 1024;
+    *chunk_out = chunk;
+    return (int)((n + chunk - 1) / chunk);
 }
 
 struct StepPlan {
@@ -1002,14 +1016,8 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
     for (Shard &s : h->shards) {
         if (s.n == 0) continue;
         CK(cudaSetDevice(s.dev));
-        int64_t chunk = std::max<int64_t>((s.n + 7) / 8, 1 << 17);
-        chunk = (chunk + 1023) / 1024 * 1024;
-        int n_chunks = (int)((s.n + chunk - 1) / chunk);
-        if (n_chunks > IO_MAX_CHUNKS) {
-            n_chunks = IO_MAX_CHUNKS;
-            chunk = ((s.n + n_chunks - 1) / n_chunks + 1023) / 1024 * 1024;
-            n_chunks = (int)((s.n + chunk - 1) / chunk);
-        }
+        int64_t chunk = 0;
+        const int n_chunks = io_chunks(s.n, &chunk);
         while ((int)s.io_in.size() < n_chunks) {
             cudaEvent_t e;
             CK(cudaEventCreate(&e)); s.io_in.push_back(e);
@@ -1048,13 +1056,8 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
         CK(cudaSetDevice(s.dev));
         CK(cudaStreamSynchronize(s.s_out));
         if (times) {
-            int64_t chunk = std::max<int64_t>((s.n + 7) / 8, 1 << 17);
-            chunk = (chunk + 1023) / 1024 * 1024;
-            int n_chunks = (int)((s.n + chunk - 1) / chunk);
-            if (n_chunks > IO_MAX_CHUNKS) {
-                chunk = ((s.n + IO_MAX_CHUNKS - 1) / IO_MAX_CHUNKS + 1023) / 1024 * 1024;
-                n_chunks = (int)((s.n + chunk - 1) / chunk);
-            }
+            int64_t chunk = 0;
+            const int n_chunks = io_chunks(s.n, &chunk);
             float tot = 0, kern = 0, h2d = 0, d2h = 0, f = 0;
             CK(cudaEventElapsedTime(&tot, s.ev_b, s.io_out[n_chunks - 1]));
             CK(cudaEventElapsedTime(&h2d, s.ev_b, s.io_in[n_chunks - 1]));

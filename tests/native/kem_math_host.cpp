@@ -67,4 +67,27 @@ double kem_check_div(long n, int emax, uint64_t seed, double *rcp_worst_out)
     return worst;
 }
 
+double kem_host_log(double x) { return kem::log(x); }
+double kem_host_sqrt(double x) { return kem::sqrt(x); }
+double kem_host_pow15(double x) { return kem::pow15(x); }
+
+// which: 0 log, 1 sqrt, 2 pow15; x log-uniform in 2^[-emax, emax] (log: also a dense sweep near 1)
+double kem_check_unary(int which, long n, int emax, uint64_t seed)
+{
+    uint64_t s = seed ? seed : 88172645463325252ull;
+    double worst = 0.0;
+    for (long i = 0; i < n; ++i) {
+        double x = ldexp(uniform(s, 1.0, 2.0), (int)(next(s) % (2 * emax + 1)) - emax);
+        if (which == 0 && (i & 3) == 0) x = uniform(s, 0.5, 2.0);
+        double got;
+        long double want;
+        if (which == 0) { got = kem::log(x); want = logl((long double)x); }
+        else if (which == 1) { got = kem::sqrt(x); want = sqrtl((long double)x); }
+        else { got = kem::pow15(x); want = powl((long double)x, 1.5L); }
+        const double e = ulp_err(got, want);
+        worst = e > worst ? e : worst;
+    }
+    return worst;
+}
+
 }  // extern "C"

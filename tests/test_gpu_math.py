@@ -17,13 +17,13 @@ SRC = textwrap.dedent('''
     def init_state_values(**values):
         return np.array([0.0, 1.0], dtype=np.float64)
     def init_parameter_values(**values):
-        return np.array([0.0, 0.0, 0.0, 0.0], dtype=np.float64)
+        return np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0], dtype=np.float64)
     def state_indices(*names):
         d = {"V": 0, "w": 1}
         r = [d[n] for n in names]
         return r if len(r) > 1 else r[0]
     def parameter_indices(*names):
-        d = {"o_exp": 0, "o_div": 1, "o_rcp": 2, "o_sing": 3}
+        d = {"o_exp": 0, "o_div": 1, "o_rcp": 2, "o_sing": 3, "o_log": 4, "o_sqrt": 5, "o_p15": 6}
         r = [d[n] for n in names]
         return r if len(r) > 1 else r[0]
     def rhs_numba(t, states, values, parameters):
@@ -31,6 +31,9 @@ SRC = textwrap.dedent('''
         parameters[1] = states[0] / states[1]
         parameters[2] = 1.0 / states[1]
         parameters[3] = states[0] / (math.exp(states[0]) - 1.0)
+        parameters[4] = math.log(states[1] * states[1])
+        parameters[5] = np.sqrt(states[1] * states[1])
+        parameters[6] = (states[1] * states[1]) ** 1.5
         values[0] = 0.0 * states[0]
         values[1] = 0.0 * states[1]
 ''')
@@ -72,6 +75,13 @@ def test_device_exp_div_rcp_within_one_ulp_of_libm(built, tmp_path):
         err_libm = np.abs(libm[:, col].astype(np.longdouble) - want) / ulp
         assert err_fast.max() <= 1.0, (col, float(err_fast.max()))
         assert err_libm.max() <= 1.0, (col, float(err_libm.max()))
+    w2 = (w * w).astype(np.longdouble)       # w*w is what the device squared, rounded to double
+    for col, want, bound in ((4, np.log(w2), 1.0), (5, np.sqrt(w2), 0.5 + 1e-9), (6, w2 * np.sqrt(w2), 1.3)):
+        ulp = np.spacing(np.abs(want.astype(np.float64)))
+        err_fast = np.abs(fast[:, col].astype(np.longdouble) - want) / ulp
+        assert err_fast.max() <= bound, (col, float(err_fast.max()))
+        err_libm = np.abs(libm[:, col].astype(np.longdouble) - want) / ulp
+        assert err_libm.max() <= 2.0, (col, float(err_libm.max()))
     # division is correctly rounded in both builds -> identical bits; the one-step cubic
     # reciprocal is faithful (<= 0.51 ulp): it may differ from IEEE in the last bit, rarely
     assert np.array_equal(fast[:, 1], libm[:, 1])

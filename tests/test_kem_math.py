@@ -27,6 +27,11 @@ def hostlib(tmp_path_factory):
         getattr(L, f).argtypes = [C.c_double]
     L.kem_host_div.restype = C.c_double
     L.kem_host_div.argtypes = [C.c_double, C.c_double]
+    L.kem_check_unary.restype = C.c_double
+    L.kem_check_unary.argtypes = [C.c_int, C.c_long, C.c_int, C.c_uint64]
+    for f in ("kem_host_log", "kem_host_sqrt", "kem_host_pow15"):
+        getattr(L, f).restype = C.c_double
+        getattr(L, f).argtypes = [C.c_double]
     return L
 
 
@@ -66,3 +71,22 @@ def test_removable_singularity_form_stays_comparable(hostlib):
         ref = x / (math.exp(x) - 1.0)
         got = hostlib.kem_host_div(x, hostlib.kem_host_exp(x) - 1.0)
         assert abs(got - ref) / abs(ref) < 2.3e-16 / abs(x) * 2
+
+
+@pytest.mark.parametrize("which,name,bound", [(0, "log", 1.0), (1, "sqrt", 0.5 + 1e-9), (2, "pow15", 1.3)])
+@pytest.mark.parametrize("emax", [1, 60, 600])
+def test_log_sqrt_pow15_accuracy(hostlib, which, name, bound, emax):
+    """log < 1 ulp; sqrt correctly rounded; x**1.5 = x*sqrt(x) <= 1.3 ulp (CUDA pow: 2 ulp)."""
+    assert hostlib.kem_check_unary(which, 300000, emax, 11) <= bound
+
+
+def test_log_special_values(hostlib):
+    assert hostlib.kem_host_log(1.0) == 0.0
+    assert hostlib.kem_host_log(0.0) == -math.inf
+    assert math.isnan(hostlib.kem_host_log(-1.0))
+    assert math.isnan(hostlib.kem_host_log(float("nan")))
+    assert hostlib.kem_host_log(math.inf) == math.inf
+    assert hostlib.kem_host_log(2.2250738585072014e-308) == math.log(2.2250738585072014e-308)
+    assert hostlib.kem_host_log(1.7976931348623157e308) == math.log(1.7976931348623157e308)
+    assert math.isnan(hostlib.kem_host_sqrt(-1.0))
+    assert hostlib.kem_host_sqrt(4.0) == 2.0
