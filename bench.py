@@ -211,6 +211,27 @@ def run_cpu_oracle(model_name: str, target_seconds: float, seed: int):
     return n * n_steps / el, threads, f"{n} DOFs x {n_steps} PDE steps of {model_name} (RK4 x {N_SUB}), {el:.1f} s"
 
 
+def run_cpu_lsoda(model_name: str, n: int, seed: int):
+    """B2 of BASELINE.md: the reference's own semantics -- serial Python loop over rows, one
+    cold-started LSODA solve per row at rtol 1e-8 / atol 1e-10 (odeSolver.py:107-122) -- with
+    scipy's LSODA standing in for the absent numbalsoda.  One core, small N; the Python
+    callback per RHS evaluation makes this 10-100x slower than numbalsoda would be."""
+    from ducks_for_tests import Space
+    from oracle.membrane_oracle import OracleMembraneModel
+    from workloads import SETUP, builtin, synthetic_tables
+    S, P, X, mask = synthetic_tables(model_name, n, seed)
+    m = OracleMembraneModel(builtin(model_name), None, 1, Space(X), oracle_name=model_name)
+    m.states[:] = S
+    m.parameters[:] = P
+    cfg = SETUP[model_name]
+    t0 = time.perf_counter()
+    m.step_lsoda_scipy(cfg["dt"], {"stim_amplitude": cfg["stim"]}, lambda x: x[0] < 20e-6)
+    el = time.perf_counter() - t0
+    return {"value": n / el, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n} DOFs x 1 PDE step of {model_name}, scipy LSODA per row, {el:.1f} s",
+            "caveat": "Python callback per RHS evaluation; numbalsoda itself would be 10-100x faster"}
+
+
 def _stim_col(model_name):
     from workloads import builtin
     return builtin(model_name).parameter_indices("stim_amplitude")
@@ -425,7 +446,9 @@ def run_gpu(args, dist: Dist):
     cpu = None
     if dist.rank == 0 and dist.world == 1 and not args.no_cpu_baseline:
         v, threads, sample = run_cpu_oracle(model_name, args.cpu_seconds, 20240611)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+               "scheme": f"O1: RK4 x {N_SUB}, the scheme the GPU runs (apples to apples)",
+               "reference_semantics_lsoda": run_cpu_lsoda(model_name, 1500, 20240611)}
 
     if dist.rank == 0:
         line = {

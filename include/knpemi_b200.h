@@ -139,6 +139,27 @@ int kem_launch_count(kem_handle h, int64_t *n_out);
 int kem_timer_begin(kem_handle h);
 int kem_timer_end(kem_handle h, double *ms_out);
 
+/* ---- device-resident PDE vectors -------------------------
+ * For a PDE side whose coefficient vectors already live on the GPU: the seven setter
+ * copies and four getter copies of one PDE step (utils.py:217-233, run_2D.py:105-109)
+ * become index gathers / scatters over membrane-DOF -> bulk-DOF maps (a CG-1 trace is a
+ * vertex copy: utils.py:150-207), with no host traffic.  Maps are registered once;
+ * `shard` selects the handle's k-th device, and the device pointers must live there. */
+/* register map `map_id` (0..15): bulk index of every membrane DOF, n = n_dof entries */
+int kem_device_map_set(kem_handle h, int map_id, const int64_t *host_map, int64_t n);
+/* table[i, col] = dev_src[map[i]]             (update_ode_variables, utils.py:224-228) */
+int kem_device_gather(kem_handle h, int shard, int kind, int col, const double *dev_src, int map_id);
+/* dev_dst[map[i]] = table[i, col]             (get_membrane_potential / get_parameter) */
+int kem_device_scatter(kem_handle h, int shard, int kind, int col, double *dev_dst, int map_id);
+/* table[i, col] = dev_a[map_a[i]] - dev_b[map_b[i]]   (phi_M = tr(phi_i) - tr(phi_e), utils.py:247-293) */
+int kem_device_gather_diff(kem_handle h, int shard, int kind, int col, const double *dev_a,
+                           int map_a, const double *dev_b, int map_b);
+/* plain device buffers for callers without their own CUDA allocations (tests, Python hosts) */
+int kem_device_alloc(int dev, size_t bytes, void **ptr_out);
+int kem_device_free(int dev, void *ptr);
+int kem_device_upload(int dev, void *dev_dst, const void *host_src, size_t bytes);
+int kem_device_download(int dev, void *host_dst, const void *dev_src, size_t bytes);
+
 /* ---- pinned host memory for callers that want zero-staging transfers ---------- */
 int kem_host_alloc(void **ptr_out, size_t bytes);
 int kem_host_free(void *ptr);

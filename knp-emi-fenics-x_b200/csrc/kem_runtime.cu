@@ -83,6 +83,33 @@ __global__ void k_copy(double2 *__restrict__ dst, const double2 *__restrict__ sr
     for (; i < n2; i += stride) dst[i] = src[i];
 }
 
+// f1 / f3: membrane <- bulk gathers and bulk <- membrane scatters (HBM-bound, 8 B + 8 B index
+// read and 8 B written per DOF; the membrane side is coalesced, the bulk side follows the map)
+__global__ void k_gather(double *__restrict__ dst, const double *__restrict__ src,
+                         const long long *__restrict__ map, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = src[map[i]];
+}
+
+__global__ void k_scatter(double *__restrict__ dst, const double *__restrict__ src,
+                          const long long *__restrict__ map, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[map[i]] = src[i];
+}
+
+__global__ void k_gather_diff(double *__restrict__ dst, const double *__restrict__ a,
+                              const long long *__restrict__ map_a, const double *__restrict__ b,
+                              const long long *__restrict__ map_b, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = a[map_a[i]] - b[map_b[i]];
+}
+
 // FP64 pipe peak: 8 independent DFMA chains per thread, nothing else in the loop.
 constexpr int PEAK_CHAINS = 8;
 constexpr int PEAK_ITERS = 8192;
@@ -132,6 +159,7 @@ constexpr size_t SMALL_BYTES = 64 * 1024;
 constexpr int N_STAGE = 3;
 constexpr size_t STAGE_BYTES = 8u << 20;
 constexpr int IO_MAX_CHUNKS = 64;
+constexpr int KEM_MAX_MAPS = 16;
 constexpr int IO_TARGET_CHUNKS = 16;   // measured best of 8/16/32/64 at 1e7 DOFs (profiles/r1_bench.md)
 
 struct Shard {
@@ -159,6 +187,8 @@ struct Shard {
     cudaEvent_t stage_ev[N_STAGE] = {};
     // per-chunk events of kem_step_io
     std::vector<cudaEvent_t> io_in, io_k0, io_k1, io_out;
+    // membrane-DOF -> bulk-DOF maps of the device-resident exchange (f1/f3)
+    long long *d_map[KEM_MAX_MAPS] = {};
 };
 
 }  // namespace
@@ -685,6 +715,7 @@ int kem_destroy(kem_handle h)
         if (s.d_mask) cudaFree(s.d_mask);
         if (s.d_ttab) cudaFree(s.d_ttab);
         if (s.d_flags) cudaFree(s.d_flags);
+        for (long long *m : s.d_map) if (m) cudaFree(m);
         if (s.h_flags) cudaFreeHost(s.h_flags);
         for (int r = 0; r < SMALL_RING; ++r) {
             if (s.h_small[r]) cudaFreeHost(s.h_small[r]);
@@ -1126,6 +1157,125 @@ int kem_launch_count(kem_handle h, int64_t *n_out)
 {
     ARG(h && n_out, "null argument");
     *n_out = h->launches;
+    return KEM_OK;
+}
+
+// ------------------------------------------------- device-resident exchange (f1, f3)
+int kem_device_map_set(kem_handle h, int map_id, const int64_t *host_map, int64_t n)
+{
+    ARG(h, "null handle");
+    ARG(map_id >= 0 && map_id < KEM_MAX_MAPS, "map_id out of range");
+    ARG(n == h->n, "length must equal the handle's n_dof");
+    ARG(host_map || n == 0, "null map");
+    for (int64_t i = 0; i < n; ++i) ARG(host_map[i] >= 0, "negative bulk index in map");
+    for (Shard &s : h->shards) {
+        if (s.n == 0) continue;
+        CK(cudaSetDevice(s.dev));
+        if (!s.d_map[map_id]) CK(cudaMalloc(&s.d_map[map_id], (size_t)s.n * sizeof(long long)));
+        CK(cudaMemcpyAsync(s.d_map[map_id], host_map + s.begin, (size_t)s.n * sizeof(long long),
+                           cudaMemcpyHostToDevice, s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+    }
+    return KEM_OK;
+}
+
+static int device_xfer_check(kem_handle h, int shard, int kind, int col, const void *p, int map_id,
+                             const char *fn)
+{
+    int rc = check_col(h, kind, col, fn);
+    if (rc) return rc;
+    if (shard < 0 || shard >= (int)h->shards.size()) return fail(KEM_E_ARG, std::string(fn) + ": shard out of range");
+    if (map_id < 0 || map_id >= KEM_MAX_MAPS || (!h->shards[shard].d_map[map_id] && h->shards[shard].n > 0))
+        return fail(KEM_E_ARG, std::string(fn) + ": map not registered (kem_device_map_set)");
+    if (!p && h->shards[shard].n > 0) return fail(KEM_E_ARG, std::string(fn) + ": null device pointer");
+    return KEM_OK;
+}
+
+int kem_device_gather(kem_handle h, int shard, int kind, int col, const double *dev_src, int map_id)
+{
+    int rc = device_xfer_check(h, shard, kind, col, dev_src, map_id, __func__);
+    if (rc) return rc;
+    if (kind == KEM_PARAM && (h->p_uniform[col] || !h->shards[0].pcol[col])) {
+        rc = ensure_pcol(h, col);
+        if (rc) return rc;
+    }
+    Shard &s = h->shards[shard];
+    if (s.n == 0) return KEM_OK;
+    CK(cudaSetDevice(s.dev));
+    k_gather<<<grid_for(s.n), 256, 0, s.stream>>>(col_ptr(s, kind, col), dev_src, s.d_map[map_id], s.n);
+    CK(cudaGetLastError());
+    h->launches++;
+    return KEM_OK;
+}
+
+int kem_device_scatter(kem_handle h, int shard, int kind, int col, double *dev_dst, int map_id)
+{
+    int rc = device_xfer_check(h, shard, kind, col, dev_dst, map_id, __func__);
+    if (rc) return rc;
+    Shard &s = h->shards[shard];
+    if (s.n == 0) return KEM_OK;
+    CK(cudaSetDevice(s.dev));
+    if (kind == KEM_PARAM && h->p_uniform[col]) {
+        rc = ensure_pcol(h, col);       // materialise the uniform value as a column first
+        if (rc) return rc;
+    }
+    k_scatter<<<grid_for(s.n), 256, 0, s.stream>>>(dev_dst, col_ptr(s, kind, col), s.d_map[map_id], s.n);
+    CK(cudaGetLastError());
+    h->launches++;
+    return KEM_OK;
+}
+
+int kem_device_gather_diff(kem_handle h, int shard, int kind, int col, const double *dev_a, int map_a,
+                           const double *dev_b, int map_b)
+{
+    int rc = device_xfer_check(h, shard, kind, col, dev_a, map_a, __func__);
+    if (rc) return rc;
+    rc = device_xfer_check(h, shard, kind, col, dev_b, map_b, __func__);
+    if (rc) return rc;
+    if (kind == KEM_PARAM && (h->p_uniform[col] || !h->shards[0].pcol[col])) {
+        rc = ensure_pcol(h, col);
+        if (rc) return rc;
+    }
+    Shard &s = h->shards[shard];
+    if (s.n == 0) return KEM_OK;
+    CK(cudaSetDevice(s.dev));
+    k_gather_diff<<<grid_for(s.n), 256, 0, s.stream>>>(col_ptr(s, kind, col), dev_a, s.d_map[map_a],
+                                                       dev_b, s.d_map[map_b], s.n);
+    CK(cudaGetLastError());
+    h->launches++;
+    return KEM_OK;
+}
+
+int kem_device_alloc(int dev, size_t bytes, void **ptr_out)
+{
+    ARG(ptr_out, "null output");
+    *ptr_out = nullptr;
+    CK(cudaSetDevice(dev));
+    CK(cudaMalloc(ptr_out, std::max<size_t>(bytes, 8)));
+    return KEM_OK;
+}
+
+int kem_device_free(int dev, void *ptr)
+{
+    CK(cudaSetDevice(dev));
+    if (ptr) CK(cudaFree(ptr));
+    return KEM_OK;
+}
+
+int kem_device_upload(int dev, void *dev_dst, const void *host_src, size_t bytes)
+{
+    ARG((dev_dst && host_src) || bytes == 0, "null pointer");
+    CK(cudaSetDevice(dev));
+    CK(cudaMemcpy(dev_dst, host_src, bytes, cudaMemcpyHostToDevice));
+    return KEM_OK;
+}
+
+int kem_device_download(int dev, void *host_dst, const void *dev_src, size_t bytes)
+{
+    ARG((host_dst && dev_src) || bytes == 0, "null pointer");
+    CK(cudaSetDevice(dev));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost));
     return KEM_OK;
 }
 

@@ -81,6 +81,15 @@ SIGNATURES = {
     "kem_timer_end": (C.c_int, [_H, _DP]),
     "kem_set_block": (C.c_int, [_H, C.c_int]),
     "kem_launch_count": (C.c_int, [_H, C.POINTER(C.c_int64)]),
+    "kem_device_map_set": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_int64]),
+    "kem_device_gather": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "kem_device_scatter": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "kem_device_gather_diff": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_int]),
+    "kem_device_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "kem_device_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "kem_device_upload": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "kem_device_download": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "kem_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "kem_host_free": (C.c_int, [C.c_void_p]),
     "kem_fp64_peak": (C.c_int, [C.c_int, _DP, _DP]),
@@ -178,3 +187,34 @@ def hbm_copy_peak(dev: int = 0) -> float:
     g = C.c_double()
     check(lib().kem_hbm_copy_peak(dev, C.byref(g)), "kem_hbm_copy_peak")
     return g.value
+
+
+class DeviceArray:
+    """float64 buffer in the HBM of one device (kem_device_alloc) -- stands in for a PDE
+    coefficient vector that already lives on the GPU (rows f1/f3 of SURVEY.md 8f)."""
+
+    def __init__(self, dev: int, host: np.ndarray):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        self.dev, self.n = dev, len(host)
+        p = C.c_void_p()
+        check(lib().kem_device_alloc(dev, host.nbytes, C.byref(p)), "kem_device_alloc")
+        self.ptr = p.value
+        check(lib().kem_device_upload(dev, C.c_void_p(self.ptr), host.ctypes.data, host.nbytes),
+              "kem_device_upload")
+
+    def to_host(self) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.float64)
+        check(lib().kem_device_download(self.dev, out.ctypes.data, C.c_void_p(self.ptr), out.nbytes),
+              "kem_device_download")
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().kem_device_free(self.dev, C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -335,6 +335,34 @@ class MembraneModel:
                                 "ms_h2d": times.ms_h2d, "ms_d2h": times.ms_d2h}
         return self.last_step_times
 
+    # ------------------------------------------- device-resident PDE vectors (f1, f3)
+    def register_trace_map(self, map_id, bulk_indices):
+        '''Bulk-DOF index of every membrane DOF (a CG-1 trace is a vertex copy, utils.py:150-207).'''
+        idx = np.ascontiguousarray(bulk_indices, dtype=np.int64)
+        check(self._lib.kem_device_map_set(self._h, int(map_id), idx.ctypes.data, self.nodes),
+              "kem_device_map_set")
+
+    def gather_from_device(self, what, which, dev_ptr, map_id, shard=0):
+        '''table[:, which] = bulk[map]  with `bulk` a device pointer: set_state/set_parameter
+        without the host round trip.'''
+        kind, col = self._kind_col(what, which)
+        check(self._lib.kem_device_gather(self._h, shard, kind, col, C.c_void_p(dev_ptr), int(map_id)),
+              "kem_device_gather")
+        return self.states
+
+    def scatter_to_device(self, what, which, dev_ptr, map_id, shard=0):
+        '''bulk[map] = table[:, which]: get_state/get_parameter into a device vector.'''
+        kind, col = self._kind_col(what, which)
+        check(self._lib.kem_device_scatter(self._h, shard, kind, col, C.c_void_p(dev_ptr), int(map_id)),
+              "kem_device_scatter")
+
+    def set_membrane_potential_from_device(self, phi_i_ptr, map_i, phi_e_ptr, map_e, shard=0):
+        '''V = tr(phi_i) - tr(phi_e) on the device (update_pde_variables, utils.py:247-293).'''
+        kind, col = self._kind_col('state', 'V')
+        check(self._lib.kem_device_gather_diff(self._h, shard, kind, col, C.c_void_p(phi_i_ptr), int(map_i),
+                                               C.c_void_p(phi_e_ptr), int(map_e)), "kem_device_gather_diff")
+        return self.states
+
     # ------------------------------------------------------------------ helpers
     def timer_begin(self):
         '''Record a CUDA event on every device's launching stream.'''

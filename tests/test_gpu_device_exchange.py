@@ -1,0 +1,55 @@
+"""PDE<->ODE exchange with device-resident bulk vectors.
+Oracle: NumPy fancy indexing (what the CG-1 trace + setter of the reference amount to)."""
+import numpy as np
+import pytest
+
+from ducks_for_tests import Func, Space
+from workloads import SETUP, builtin, load_tables, synthetic_tables
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gather_scatter_and_potential_jump(built):
+    from knpemi_b200._cabi import DeviceArray, KemError
+    from knpemi_b200.odeSolver import MembraneModel
+    name, n, n_bulk = "hh_ideal", 50_003, 400_000
+    rng = np.random.default_rng(0)
+    S, P, X, mask = synthetic_tables(name, n, seed=3)
+    ode = builtin(name)
+    a = MembraneModel(ode, None, 1, Space(X), verbose=False, devices=[0])     # device-resident exchange
+    b = MembraneModel(ode, None, 1, Space(X), verbose=False, devices=[0])     # host setters/getters
+    for m in (a, b):
+        load_tables(m, S, P)
+    map_e = rng.choice(n_bulk, n, replace=False)
+    map_i = rng.choice(n_bulk, n, replace=False)
+    a.register_trace_map(0, map_e)
+    a.register_trace_map(1, map_i)
+    K_e_bulk = 3.3 * (1 + 0.02 * rng.uniform(-1, 1, n_bulk))
+    phi_e = 1e-3 * rng.normal(size=n_bulk)
+    phi_i = -0.07 + 1e-3 * rng.normal(size=n_bulk)
+    d_K, d_pe, d_pi = DeviceArray(0, K_e_bulk), DeviceArray(0, phi_e), DeviceArray(0, phi_i)
+    a.gather_from_device('parameter', 'K_e', d_K.ptr, 0)
+    a.set_membrane_potential_from_device(d_pi.ptr, 1, d_pe.ptr, 0)
+    b.set_parameter('K_e', Func(K_e_bulk[map_e]))
+    b.set_membrane_potential(Func(phi_i[map_i] - phi_e[map_e]))
+    for m in (a, b):
+        m.step_lsoda(1e-4, {'stim_amplitude': 10.0}, lambda x: x[0] < 20e-6)
+    assert np.array_equal(np.asarray(a.states), np.asarray(b.states))
+    assert np.array_equal(np.asarray(a.parameters), np.asarray(b.parameters))
+    # ODE -> PDE: scatter I_ch_Na into a bulk-sized device vector
+    d_out = DeviceArray(0, np.zeros(n_bulk))
+    a.scatter_to_device('parameter', 'I_ch_Na', d_out.ptr, 1)
+    want = np.zeros(n_bulk)
+    want[map_i] = b.parameters[:, ode.parameter_indices('I_ch_Na')]
+    assert np.array_equal(d_out.to_host(), want)
+    # a uniform column scatters its value
+    a.scatter_to_device('parameter', 'Cm', d_out.ptr, 1)
+    assert np.all(d_out.to_host()[map_i] == SETUP[name]["uniform"]["Cm"])
+    with pytest.raises(KemError, match="map not registered"):
+        a.gather_from_device('parameter', 'K_e', d_K.ptr, 5)
+    with pytest.raises(KemError):
+        a.register_trace_map(2, -np.ones(n, dtype=np.int64))
+    for d in (d_K, d_pe, d_pi, d_out):
+        d.free()
+    a.close()
+    b.close()
