@@ -34,7 +34,9 @@ extern "C" {
 #define KEM_STATE 0      /* `what == 'state'`     odeSolver.py:133 */
 #define KEM_PARAM 1      /* `what == 'parameter'` odeSolver.py:134 */
 
-#define KEM_SCHEME_RK4 0 /* scheme O1: classical RK4, n_sub sub-steps + current epilogue */
+#define KEM_SCHEME_RK4 0  /* scheme O1: classical RK4, n_sub sub-steps + current epilogue */
+#define KEM_SCHEME_DP45 1 /* scheme O3: Dormand-Prince 5(4), per-DOF error-controlled steps
+                             (the reference's LSODA is error-controlled too: odeSolver.py:116-120) */
 
 typedef struct kem_handle_s *kem_handle;
 
@@ -128,6 +130,12 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme,
                 int n_in, const kem_io_column *in, int n_out, const kem_io_column *out,
                 int *status_flags, kem_step_times *times_out);
 int kem_sync(kem_handle h);
+/* tolerances of KEM_SCHEME_DP45; defaults are the reference's rtol 1e-8, atol 1e-10
+ * (odeSolver.py:120) */
+int kem_set_tolerances(kem_handle h, double rtol, double atol);
+/* accepted / rejected DP45 steps summed over all DOFs since the last call (waits for the
+ * device); RHS evaluations = 6 * (accepted + rejected) + 1 per DOF-step */
+int kem_get_step_stats(kem_handle h, uint64_t *accepted_out, uint64_t *rejected_out);
 /* launch configuration knobs: threads per block (64/128/256; 0 = model default) */
 int kem_set_block(kem_handle h, int block);
 /* number of kernels this handle has launched since creation */

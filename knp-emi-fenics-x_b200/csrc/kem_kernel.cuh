@@ -38,32 +38,23 @@ struct KemArgs {
     int n_sub;
     double h;
     int *flags;
+    // scheme O3 (Dormand-Prince 5(4))
+    double t0, dt, t_end, rtol, atol;
+    double *hsug;
+    unsigned long long *stats;
 };
 
-template <class M, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
-kem_step_kernel(const __grid_constant__ KemArgs<M> a)
+// Prologue shared by the step kernels: parameters of DOF i (only the slots the RHS
+// reads), sticky stimulus (odeSolver.py:110-112), parameter-only sub-expressions.
+template <class M>
+__device__ __forceinline__ void kem_prologue(const KemArgs<M> &a, long long i, typename M::H &q)
 {
-    constexpr int NS = M::NS, NP = M::NP, NOUT = M::NOUT, NT = M::NT;
-    extern __shared__ double s_tt[];
-
-    // time-only factors of every stage time of this PDE step (host-evaluated)
-    if (NT > 0) {
-        const int n_tt = (2 * a.n_sub + 2) * NT;
-        for (int k = threadIdx.x; k < n_tt; k += BLOCK) s_tt[k] = a.ttab[k];
-        __syncthreads();
-    }
-
-    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= a.n) return;
-
-    // ---- parameters of this DOF (only the slots the RHS reads)
+    constexpr int NP = M::NP;
     double p[NP];
 #pragma unroll
     for (int c = 0; c < NP; ++c)
         p[c] = M::used(c) ? __ldg(a.p[c] + (i & a.pmask[c])) : 0.0;
 
-    // ---- sticky stimulus (odeSolver.py:110-112)
     if (a.n_stim > 0 && a.stim_mask[i]) {
 #pragma unroll
         for (int s = 0; s < KEM_MAX_STIM; ++s) {
@@ -77,10 +68,29 @@ kem_step_kernel(const __grid_constant__ KemArgs<M> a)
             }
         }
     }
-
-    // ---- parameter-only sub-expressions, once per PDE step
-    typename M::H q;
     M::hoist(p, q);
+}
+
+template <class M, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+kem_step_kernel(const __grid_constant__ KemArgs<M> a)
+{
+    constexpr int NS = M::NS, NOUT = M::NOUT, NT = M::NT;
+    extern __shared__ double s_tt[];
+
+    // time-only factors of every stage time of this PDE step (host-evaluated)
+    if (NT > 0) {
+        const int n_tt = (2 * a.n_sub + 2) * NT;
+        for (int k = threadIdx.x; k < n_tt; k += BLOCK) s_tt[k] = a.ttab[k];
+        __syncthreads();
+    }
+
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= a.n) return;
+
+    // ---- parameters, sticky stimulus, parameter-only sub-expressions (once per PDE step)
+    typename M::H q;
+    kem_prologue<M>(a, i, q);
 
     double y[NS];
 #pragma unroll
@@ -140,6 +150,152 @@ kem_step_kernel(const __grid_constant__ KemArgs<M> a)
     if (!finite) atomicOr(a.flags, 1);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Scheme O3: error-controlled Dormand-Prince 5(4), one thread = one DOF, step sizes per DOF.
+// Device twin of oracle/knpemi_oracle.c:dp45_row (same formulas, same association; the
+// time logic uses non-contracted adds/multiplies so both sides see bit-identical stage
+// times).  Time-only factors are evaluated on the device per stage (M::tonly_dev) because the
+// stage times are not known on the host.  A warp runs until its slowest lane has reached
+// t_end; lanes that are done idle (DOF numbering is spatially coherent on real meshes, so
+// quiescent and active DOFs mostly sit in different warps).
+template <class M, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+kem_step_dp45_kernel(const __grid_constant__ KemArgs<M> a)
+{
+    constexpr int NS = M::NS, NOUT = M::NOUT, NT = M::NT;
+    const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= a.n) return;
+
+    typename M::H q;
+    kem_prologue<M>(a, i, q);
+
+    double y[NS];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) y[c] = a.y[c][i];
+
+    constexpr double c2 = 1.0 / 5.0, c3 = 3.0 / 10.0, c4 = 4.0 / 5.0, c5 = 8.0 / 9.0;
+    constexpr double a21 = 1.0 / 5.0;
+    constexpr double a31 = 3.0 / 40.0, a32 = 9.0 / 40.0;
+    constexpr double a41 = 44.0 / 45.0, a42 = -56.0 / 15.0, a43 = 32.0 / 9.0;
+    constexpr double a51 = 19372.0 / 6561.0, a52 = -25360.0 / 2187.0, a53 = 64448.0 / 6561.0,
+                     a54 = -212.0 / 729.0;
+    constexpr double a61 = 9017.0 / 3168.0, a62 = -355.0 / 33.0, a63 = 46732.0 / 5247.0,
+                     a64 = 49.0 / 176.0, a65 = -5103.0 / 18656.0;
+    constexpr double b1 = 35.0 / 384.0, b3 = 500.0 / 1113.0, b4 = 125.0 / 192.0,
+                     b5 = -2187.0 / 6784.0, b6 = 11.0 / 84.0;
+    constexpr double e1 = 71.0 / 57600.0, e3 = -71.0 / 16695.0, e4 = 71.0 / 1920.0,
+                     e5 = -17253.0 / 339200.0, e6 = 22.0 / 525.0, e7 = -1.0 / 40.0;
+
+    const double dt = a.dt, t_end = a.t_end, rtol = a.rtol, atol = a.atol;
+    double t = a.t0;
+    double h_try = a.hsug[i];
+    if (!(h_try > 0.0) || !isfinite(h_try)) h_try = dt / 8.0;
+    if (h_try > dt) h_try = dt;
+
+    double ts[NT > 0 ? NT : 1];
+    double k1[NS], k2[NS], k3[NS], k4[NS], k5[NS], k6[NS], k7[NS], w[NS], yn[NS];
+    M::tonly_dev(t, ts);
+    M::deriv(y, k1, q, ts);
+
+    bool rejected = false, failed = true;
+    unsigned n_acc = 0, n_rej = 0;
+#pragma unroll 1
+    for (int attempt = 0; attempt < 100000; ++attempt) {
+        double h = h_try;
+        bool last = false;
+        if (__dadd_rn(t, __dmul_rn(h, 1.0 + 1e-9)) >= t_end) {
+            h = __dsub_rn(t_end, t);
+            last = true;
+        }
+#pragma unroll
+        for (int c = 0; c < NS; ++c) w[c] = y[c] + h * (a21 * k1[c]);
+        M::tonly_dev(__dadd_rn(t, __dmul_rn(c2, h)), ts);
+        M::deriv(w, k2, q, ts);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) w[c] = y[c] + h * (a31 * k1[c] + a32 * k2[c]);
+        M::tonly_dev(__dadd_rn(t, __dmul_rn(c3, h)), ts);
+        M::deriv(w, k3, q, ts);
+#pragma unroll
+        for (int c = 0; c < NS; ++c) w[c] = y[c] + h * ((a41 * k1[c] + a42 * k2[c]) + a43 * k3[c]);
+        M::tonly_dev(__dadd_rn(t, __dmul_rn(c4, h)), ts);
+        M::deriv(w, k4, q, ts);
+#pragma unroll
+        for (int c = 0; c < NS; ++c)
+            w[c] = y[c] + h * (((a51 * k1[c] + a52 * k2[c]) + a53 * k3[c]) + a54 * k4[c]);
+        M::tonly_dev(__dadd_rn(t, __dmul_rn(c5, h)), ts);
+        M::deriv(w, k5, q, ts);
+#pragma unroll
+        for (int c = 0; c < NS; ++c)
+            w[c] = y[c] + h * ((((a61 * k1[c] + a62 * k2[c]) + a63 * k3[c]) + a64 * k4[c]) + a65 * k5[c]);
+        const double t_new = last ? t_end : __dadd_rn(t, h);
+        M::tonly_dev(t_new, ts);
+        M::deriv(w, k6, q, ts);
+#pragma unroll
+        for (int c = 0; c < NS; ++c)
+            yn[c] = y[c] + h * ((((b1 * k1[c] + b3 * k3[c]) + b4 * k4[c]) + b5 * k5[c]) + b6 * k6[c]);
+        M::deriv(yn, k7, q, ts);
+        double sum = 0.0;
+#pragma unroll
+        for (int c = 0; c < NS; ++c) {
+            const double ei = h * (((((e1 * k1[c] + e3 * k3[c]) + e4 * k4[c]) + e5 * k5[c]) + e6 * k6[c])
+                                   + e7 * k7[c]);
+            const double sc = atol + rtol * fmax(fabs(y[c]), fabs(yn[c]));
+            const double r = ei / sc;
+            sum += r * r;
+        }
+        const double err = sqrt(sum / (double)NS);
+        if (err <= 1.0) {
+            double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+            if (rejected) factor = fmin(1.0, factor);
+            t = t_new;
+#pragma unroll
+            for (int c = 0; c < NS; ++c) { y[c] = yn[c]; k1[c] = k7[c]; }
+            ++n_acc;
+            rejected = false;
+            const double h_next = h * factor;
+            h_try = last ? fmax(h_next, h_try) : h_next;
+            if (last) {
+                failed = false;
+                break;
+            }
+        } else {
+            const double factor = (err == err) ? fmax(0.2, 0.9 * pow(err, -0.2)) : 0.2;
+            h_try = h * factor;
+            rejected = true;
+            ++n_rej;
+            if (!(h_try > 1e-14 * fabs(dt))) break;
+        }
+    }
+    a.hsug[i] = failed ? 0.0 : (h_try > dt ? dt : h_try);
+
+    // ---- current epilogue at (t_end, y): ts still holds the factors of t_end
+    if (NOUT > 0) {
+        double o[NOUT > 0 ? NOUT : 1];
+        M::outputs(y, o, q, ts);
+#pragma unroll
+        for (int c = 0; c < NOUT; ++c) a.out[c][i] = o[c];
+    }
+    bool finite = true;
+#pragma unroll
+    for (int c = 0; c < NS; ++c) {
+        a.y[c][i] = y[c];
+        finite = finite && isfinite(y[c]);
+    }
+    if (!finite || failed) atomicOr(a.flags, 1);
+
+    // ---- step statistics: one atomic pair per warp
+    if (a.stats) {
+        const unsigned mask = __activemask();
+        const unsigned acc = __reduce_add_sync(mask, n_acc);
+        const unsigned rej = __reduce_add_sync(mask, n_rej);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(mask) - 1)) {
+            atomicAdd(a.stats, (unsigned long long)acc);
+            atomicAdd(a.stats + 1, (unsigned long long)rej);
+        }
+    }
+}
+
 template <class M, int BLOCK>
 static cudaError_t kem_launch_block(const KemArgs<M> &a, size_t smem, cudaStream_t stream)
 {
@@ -153,11 +309,22 @@ static cudaError_t kem_launch_block(const KemArgs<M> &a, size_t smem, cudaStream
     return cudaGetLastError();
 }
 
+template <class M, int BLOCK>
+static cudaError_t kem_launch_dp45_block(const KemArgs<M> &a, cudaStream_t stream)
+{
+    const long long grid = (a.n + BLOCK - 1) / BLOCK;
+    kem_step_dp45_kernel<M, BLOCK><<<(unsigned)grid, BLOCK, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
 template <class M>
 static cudaError_t kem_launch(const KemLaunch *L, cudaStream_t stream)
 {
     if (L->n <= 0) return cudaSuccess;
-    if (L->n_stim > KEM_MAX_STIM || L->n_sub < 1) return cudaErrorInvalidValue;
+    if (L->n_stim > KEM_MAX_STIM) return cudaErrorInvalidValue;
+    if (L->scheme == 0 && L->n_sub < 1) return cudaErrorInvalidValue;
+    if (L->scheme == 1 && (!L->hsug || !(L->rtol > 0.0) || !(L->atol >= 0.0))) return cudaErrorInvalidValue;
+    if (L->scheme != 0 && L->scheme != 1) return cudaErrorInvalidValue;
     if ((L->n + 63) / 64 > 0x7fffffffLL) return cudaErrorInvalidValue;
     KemArgs<M> a;
     a.n = L->n;
@@ -175,6 +342,17 @@ static cudaError_t kem_launch(const KemLaunch *L, cudaStream_t stream)
     a.n_sub = L->n_sub;
     a.h = L->h;
     a.flags = L->flags;
+    a.t0 = L->t0; a.dt = L->dt; a.t_end = L->t_end; a.rtol = L->rtol; a.atol = L->atol;
+    a.hsug = L->hsug; a.stats = L->stats;
+    if (L->scheme == 1) {
+        const int blk = L->block ? L->block : M::DEFAULT_BLOCK;
+        switch (blk) {
+            case 64:  return kem_launch_dp45_block<M, 64>(a, stream);
+            case 128: return kem_launch_dp45_block<M, 128>(a, stream);
+            case 256: return kem_launch_dp45_block<M, 256>(a, stream);
+            default:  return cudaErrorInvalidValue;
+        }
+    }
     const size_t smem = (size_t)(2 * L->n_sub + 2) * M::NT * sizeof(double);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     const int block = L->block ? L->block : M::DEFAULT_BLOCK;

@@ -11,7 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define KEM_MODEL_ABI_VERSION 3
+#define KEM_MODEL_ABI_VERSION 4
 #define KEM_MAX_STIM 4
 
 extern "C" {
@@ -35,6 +35,11 @@ typedef struct KemLaunch {
     double h;                       // dt / n_sub
     int *flags;                     // device int, OR-ed with 1 if any end state is non-finite
     int block;                      // threads per block (0 = model default)
+    int scheme;                     // 0 = RK4 x n_sub (O1), 1 = Dormand-Prince 5(4) (O3)
+    double t0, dt, t_end;           // O3: the PDE step [t0, t_end], t_end = t0 + dt formed on the host
+    double rtol, atol;              // O3: error tolerances
+    double *hsug;                   // O3: per-DOF warm-start step size (read + written)
+    unsigned long long *stats;      // O3: device counters [accepted steps, rejected steps]
 } KemLaunch;
 
 typedef struct KemModelDesc {

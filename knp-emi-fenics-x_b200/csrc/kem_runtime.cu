@@ -187,6 +187,10 @@ struct Shard {
     cudaEvent_t stage_ev[N_STAGE] = {};
     // per-chunk events of kem_step_io
     std::vector<cudaEvent_t> io_in, io_k0, io_k1, io_out;
+    // scheme O3: per-DOF warm-start step size, device counters [accepted, rejected]
+    double *d_hsug = nullptr;
+    unsigned long long *d_stats = nullptr;
+    unsigned long long *h_stats = nullptr;   // pinned
     // membrane-DOF -> bulk-DOF maps of the device-resident exchange (f1/f3)
     long long *d_map[KEM_MAX_MAPS] = {};
 };
@@ -203,6 +207,7 @@ struct kem_handle_s {
     bool uni_dirty = true;
     int block = 0;
     int64_t launches = 0;
+    double rtol = 1.0e-8, atol = 1.0e-10;   // odeSolver.py:120
 };
 
 namespace {
@@ -379,6 +384,8 @@ int io_chunks(int64_t n, int64_t *chunk_out)
 }
 
 struct StepPlan {
+    int scheme = KEM_SCHEME_RK4;
+    double t0 = 0.0, dt = 0.0, t_end = 0.0;
     int n_stim = 0;
     int stim_col[KEM_MAX_STIM];
     double stim_val[KEM_MAX_STIM];
@@ -394,14 +401,29 @@ int prepare_step(kem_handle h, double t0, double dt, int n_sub, int scheme, int 
                  const int *stim_cols, const double *stim_vals, StepPlan &pl)
 {
     ARG(h, "null handle");
-    ARG(scheme == KEM_SCHEME_RK4, "unknown scheme");
-    ARG(n_sub >= 1 && n_sub <= 100000, "n_sub out of range");
+    ARG(scheme == KEM_SCHEME_RK4 || scheme == KEM_SCHEME_DP45, "unknown scheme");
+    ARG(scheme != KEM_SCHEME_RK4 || (n_sub >= 1 && n_sub <= 100000), "n_sub out of range");
+    ARG(scheme != KEM_SCHEME_DP45 || dt > 0.0, "KEM_SCHEME_DP45 needs dt > 0");
     ARG(n_stim >= 0 && n_stim <= KEM_MAX_STIM, "too many stimulus entries");
     ARG(n_stim == 0 || (stim_cols && stim_vals), "null stimulus arrays");
     ARG(isfinite(t0) && isfinite(dt), "non-finite time");
     const KemModelDesc *m = h->m;
-    pl.n_sub = n_sub;
-    pl.hstep = dt / (double)n_sub;
+    pl.scheme = scheme;
+    pl.t0 = t0;
+    pl.dt = dt;
+    pl.t_end = t0 + dt;
+    pl.n_sub = scheme == KEM_SCHEME_RK4 ? n_sub : 0;
+    pl.hstep = scheme == KEM_SCHEME_RK4 ? dt / (double)n_sub : 0.0;
+    if (scheme == KEM_SCHEME_DP45)
+        for (Shard &s : h->shards) {
+            if (s.d_hsug) continue;
+            CK(cudaSetDevice(s.dev));
+            CK(cudaMalloc(&s.d_hsug, std::max<size_t>((size_t)s.n, 1) * sizeof(double)));
+            CK(cudaMemsetAsync(s.d_hsug, 0, std::max<size_t>((size_t)s.n, 1) * sizeof(double), s.stream));
+            CK(cudaMalloc(&s.d_stats, 2 * sizeof(unsigned long long)));
+            CK(cudaMemsetAsync(s.d_stats, 0, 2 * sizeof(unsigned long long), s.stream));
+            CK(cudaHostAlloc((void **)&s.h_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+        }
     pl.masked = !h->shards.empty() && h->shards[0].has_mask;
     for (int s = 0; s < n_stim; ++s) {
         ARG(stim_cols[s] >= 0 && stim_cols[s] < m->np, "stimulus column out of range");
@@ -419,7 +441,7 @@ int prepare_step(kem_handle h, double t0, double dt, int n_sub, int scheme, int 
             if (rc) return rc;
         }
     }
-    build_ttab(m, t0, dt, n_sub, pl.ttab);
+    if (scheme == KEM_SCHEME_RK4) build_ttab(m, t0, dt, n_sub, pl.ttab);
     for (Shard &s : h->shards) {
         CK(cudaSetDevice(s.dev));
         const size_t tb = pl.ttab.size() * sizeof(double);
@@ -480,6 +502,14 @@ int launch_range(kem_handle h, Shard &s, const StepPlan &pl, int64_t off, int64_
     L.h = pl.hstep;
     L.flags = s.d_flags;
     L.block = h->block;
+    L.scheme = pl.scheme;
+    L.t0 = pl.t0;
+    L.dt = pl.dt;
+    L.t_end = pl.t_end;
+    L.rtol = h->rtol;
+    L.atol = h->atol;
+    L.hsug = s.d_hsug ? s.d_hsug + off : nullptr;
+    L.stats = s.d_stats;
     CK(cudaSetDevice(s.dev));
     cudaError_t e = m->launch(&L, s.stream);
     if (e != cudaSuccess)
@@ -715,6 +745,9 @@ int kem_destroy(kem_handle h)
         if (s.d_mask) cudaFree(s.d_mask);
         if (s.d_ttab) cudaFree(s.d_ttab);
         if (s.d_flags) cudaFree(s.d_flags);
+        if (s.d_hsug) cudaFree(s.d_hsug);
+        if (s.d_stats) cudaFree(s.d_stats);
+        if (s.h_stats) cudaFreeHost(s.h_stats);
         for (long long *m : s.d_map) if (m) cudaFree(m);
         if (s.h_flags) cudaFreeHost(s.h_flags);
         for (int r = 0; r < SMALL_RING; ++r) {
@@ -1114,6 +1147,32 @@ int kem_sync(kem_handle h)
     if (rc) return rc;
     int flags = 0;
     return read_flags(h, &flags);
+}
+
+int kem_set_tolerances(kem_handle h, double rtol, double atol)
+{
+    ARG(h, "null handle");
+    ARG(rtol > 0.0 && atol >= 0.0 && isfinite(rtol) && isfinite(atol), "tolerances must be positive");
+    h->rtol = rtol;
+    h->atol = atol;
+    return KEM_OK;
+}
+
+int kem_get_step_stats(kem_handle h, uint64_t *accepted_out, uint64_t *rejected_out)
+{
+    ARG(h && accepted_out && rejected_out, "null argument");
+    *accepted_out = *rejected_out = 0;
+    for (Shard &s : h->shards) {
+        if (!s.d_stats) continue;
+        CK(cudaSetDevice(s.dev));
+        CK(cudaMemcpyAsync(s.h_stats, s.d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                           s.stream));
+        CK(cudaMemsetAsync(s.d_stats, 0, 2 * sizeof(unsigned long long), s.stream));
+        CK(cudaStreamSynchronize(s.stream));
+        *accepted_out += s.h_stats[0];
+        *rejected_out += s.h_stats[1];
+    }
+    return KEM_OK;
 }
 
 int kem_timer_begin(kem_handle h)

@@ -15,6 +15,7 @@ from .codegen.build import RUNTIME_LIB
 
 KEM_STATE, KEM_PARAM = 0, 1
 KEM_SCHEME_RK4 = 0
+KEM_SCHEME_DP45 = 1
 KEM_NONFINITE = 1
 KEM_MAX_STIM = 4
 
@@ -77,6 +78,8 @@ SIGNATURES = {
                               C.c_int, C.POINTER(kem_io_column), C.c_int, C.POINTER(kem_io_column),
                               _IP, C.POINTER(kem_step_times)]),
     "kem_sync": (C.c_int, [_H]),
+    "kem_set_tolerances": (C.c_int, [_H, C.c_double, C.c_double]),
+    "kem_get_step_stats": (C.c_int, [_H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "kem_timer_begin": (C.c_int, [_H]),
     "kem_timer_end": (C.c_int, [_H, _DP]),
     "kem_set_block": (C.c_int, [_H, C.c_int]),

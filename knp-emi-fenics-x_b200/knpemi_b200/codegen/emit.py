@@ -23,7 +23,7 @@ from dataclasses import dataclass
 from .ir import P, S, T, Dag, ModelSourceError
 from .parse import ParsedModel
 
-CODEGEN_VERSION = "6"
+CODEGEN_VERSION = "7"
 
 
 @dataclass
@@ -135,7 +135,7 @@ class _Emitter:
             if n.op == "param":
                 return f"p[{n.val}]"
             return self.nm(nid)
-        if ctx == "time":
+        if ctx in ("time", "time_dev"):
             if n.op == "time":
                 return "t"
             return self.nm(nid)
@@ -220,7 +220,7 @@ class _Emitter:
             n = self.dag.nodes[nid]
             if n.op in ("const", "iconst", "param", "state", "time"):
                 continue
-            if self.klass(nid) != ctx:
+            if self.klass(nid) != ("time" if ctx == "time_dev" else ctx):
                 continue
             if n.op == "powi":
                 lines += self.powi_lines(nid, ctx, indent)
@@ -330,6 +330,16 @@ class _Emitter:
         L.extend(self.section(order_out, "dyn"))
         for k, c in enumerate(self.out_cols):
             w(f"        o[{k}] = {self.operand(pm.out[c], 'dyn')};  // parameters[{c}]")
+        w("    }")
+        w("")
+        w("    // device: the same time-only factors, for schemes whose stage times are not known on")
+        w("    // the host (error-controlled stepping)")
+        w("    static __device__ __forceinline__ void tonly_dev(double t, double *ts)")
+        w("    {")
+        w("        (void)t; (void)ts;")
+        L.extend(self.section(order_time, "time_dev"))
+        for nid in time_front:
+            w(f"        ts[{self.tslot[nid]}] = {self.operand(nid, 'time_dev')};")
         w("    }")
         w("")
         w("    // host: time-only factors at stage time t (glibc libm, like the reference cfunc)")

@@ -31,8 +31,8 @@ import time as _time
 import numpy as np
 
 from . import _cabi
-from ._cabi import (KEM_PARAM, KEM_SCHEME_RK4, KEM_STATE, KemError, NonFiniteStateError, check,
-                    kem_io_column, kem_step_times)
+from ._cabi import (KEM_PARAM, KEM_SCHEME_DP45, KEM_SCHEME_RK4, KEM_STATE, KemError, NonFiniteStateError,
+                    check, kem_io_column, kem_step_times)
 from .codegen import EmitOptions, model_library
 
 __all__ = ["MembraneModel", "TableView", "KemError", "NonFiniteStateError"]
@@ -148,9 +148,9 @@ class TableView:
 class MembraneModel:
     '''ODE on membrane defined by tagged facet function (B200 backend)'''
 
-    def __init__(self, ode, ft, tag, Q, *, devices=None, n_sub=25, scheme="rk4", block=0,
-                 verbose=True, strict_locators=False, emit_options: EmitOptions | None = None,
-                 nvcc_flags=()):
+    def __init__(self, ode, ft, tag, Q, *, devices=None, n_sub=25, scheme="rk4", rtol=1.0e-8,
+                 atol=1.0e-10, block=0, verbose=True, strict_locators=False,
+                 emit_options: EmitOptions | None = None, nvcc_flags=()):
         assert isinstance(tag, int)                                   # odeSolver.py:13
 
         # all DOFs of the membrane function space are stepped (odeSolver.py:32-38; `ft` unused)
@@ -159,9 +159,12 @@ class MembraneModel:
         nodes = len(self.indices)
         self.nodes = nodes
 
-        if scheme != "rk4":
-            raise ValueError(f"unknown scheme {scheme!r}; this backend implements 'rk4' (scheme O1)")
+        if scheme not in ("rk4", "dp45"):
+            raise ValueError(f"unknown scheme {scheme!r}; this backend implements 'rk4' (scheme O1: "
+                             "classical RK4 x n_sub) and 'dp45' (scheme O3: error-controlled "
+                             "Dormand-Prince 5(4) at rtol/atol)")
         self.scheme = scheme
+        self._scheme_id = KEM_SCHEME_RK4 if scheme == "rk4" else KEM_SCHEME_DP45
         self.n_sub = int(n_sub)
         self.verbose = bool(verbose)
         self.strict_locators = bool(strict_locators)
@@ -191,6 +194,8 @@ class MembraneModel:
         self._h = h
         if block:
             check(self._lib.kem_set_block(self._h, int(block)), "kem_set_block")
+        check(self._lib.kem_set_tolerances(self._h, float(rtol), float(atol)), "kem_set_tolerances")
+        self.rtol, self.atol = float(rtol), float(atol)
 
         self.states = TableView(self, KEM_STATE, self._ns)
         self.parameters = TableView(self, KEM_PARAM, self._np)
@@ -277,12 +282,12 @@ class MembraneModel:
         flags = C.c_int(0)
         if timed:
             times = kem_step_times()
-            rc = self._lib.kem_step_timed(self._h, float(self.time), float(dt), n_sub, KEM_SCHEME_RK4,
+            rc = self._lib.kem_step_timed(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
                                           n_stim, cols, vals, C.byref(flags), C.byref(times))
             self.last_step_times = {"ms_kernel": times.ms_kernel, "ms_total": times.ms_total,
                                     "ms_h2d": times.ms_h2d, "ms_d2h": times.ms_d2h}
         else:
-            rc = self._lib.kem_step(self._h, float(self.time), float(dt), n_sub, KEM_SCHEME_RK4,
+            rc = self._lib.kem_step(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
                                     n_stim, cols, vals, C.byref(flags))
         check(rc, "kem_step")                                          # odeSolver.py:121
         self.time = self.time + dt                                     # odeSolver.py:106,123
@@ -294,7 +299,7 @@ class MembraneModel:
         '''Enqueue one step without waiting for it; errors surface at :meth:`synchronize`.'''
         cols, vals, n_stim = self._prepare_stimulus(stimulus, stimulus_locator)
         n_sub = self.n_sub if n_sub is None else int(n_sub)
-        check(self._lib.kem_step(self._h, float(self.time), float(dt), n_sub, KEM_SCHEME_RK4,
+        check(self._lib.kem_step(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
                                  n_stim, cols, vals, None), "kem_step")
         self.time = self.time + dt
         return self.states
@@ -326,7 +331,7 @@ class MembraneModel:
         a_in, a_out = pack(inputs, False), pack(outputs, True)
         flags = C.c_int(0)
         times = kem_step_times()
-        rc = self._lib.kem_step_io(self._h, float(self.time), float(dt), n_sub, KEM_SCHEME_RK4,
+        rc = self._lib.kem_step_io(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
                                    n_stim, cols, vals, len(inputs), a_in, len(outputs), a_out,
                                    C.byref(flags), C.byref(times))
         check(rc, "kem_step_io")
@@ -373,6 +378,12 @@ class MembraneModel:
         ms = C.c_double(0.0)
         check(self._lib.kem_timer_end(self._h, C.byref(ms)), "kem_timer_end")
         return ms.value
+
+    def step_stats(self):
+        '''(accepted, rejected) DP45 steps over all DOFs since the last call.'''
+        a, r = C.c_uint64(0), C.c_uint64(0)
+        check(self._lib.kem_get_step_stats(self._h, C.byref(a), C.byref(r)), "kem_get_step_stats")
+        return a.value, r.value
 
     def launch_count(self):
         n = C.c_int64(0)

@@ -52,6 +52,10 @@ def lib() -> ctypes.CDLL:
                                    _DP, _DP, ctypes.c_double, ctypes.c_double,
                                    ctypes.c_int, ctypes.c_int]
         L.kemo_step_fn.restype = ctypes.c_int64
+        L.kemo_step_dp45.argtypes = [ctypes.c_int, ctypes.c_int64, _DP, _DP, _DP, ctypes.c_double,
+                                     ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_int64)]
+        L.kemo_step_dp45.restype = ctypes.c_int64
         L.kemo_max_threads.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -102,6 +106,18 @@ def step_fn(address: int, states: np.ndarray, params: np.ndarray, t0: float, dt:
     return int(lib().kemo_step_fn(ctypes.c_void_p(address), states.shape[1], params.shape[1],
                                   states.shape[0], _ptr(states), _ptr(params),
                                   float(t0), float(dt), int(n_sub), int(n_threads)))
+
+
+def step_dp45(name: str, states: np.ndarray, params: np.ndarray, hsug: np.ndarray, t0: float, dt: float,
+              rtol: float = 1e-8, atol: float = 1e-10, n_threads: int = 0):
+    """Scheme O3 (Dormand-Prince 5(4), error-controlled) IN PLACE; returns (#failed rows,
+    accepted steps, rejected steps).  `hsug` is the per-row warm-start step size (in/out)."""
+    ns, np_ = dims(name)
+    assert states.shape[1] == ns and params.shape == (states.shape[0], np_) and hsug.shape == (states.shape[0],)
+    stats = (ctypes.c_int64 * 2)()
+    bad = lib().kemo_step_dp45(model_id(name), states.shape[0], _ptr(states), _ptr(params), _ptr(hsug),
+                               float(t0), float(dt), float(rtol), float(atol), int(n_threads), stats)
+    return int(bad), int(stats[0]), int(stats[1])
 
 
 def max_threads() -> int:

@@ -453,6 +453,134 @@ int64_t kemo_step(int model, int64_t n, double *states, double *params,
                         n, states, params, t0, dt, n_sub, n_threads);
 }
 
+/* ------------------------------------------------------------------ scheme O3
+ * Error-controlled alternative to O1: Dormand-Prince 5(4) with
+ * the step-size controller of scipy.integrate.RK45 (error norm = RMS of
+ * e_i / (atol + rtol max(|y_i|, |ynew_i|)), factor = 0.9 err^(-1/5) in [0.2, 10], no growth
+ * right after a rejection), restarted every PDE step like the reference restarts LSODA
+ * (odeSolver.py:116-120) but warm-started from the step size the DOF last used (`hsug`,
+ * one double per row, in/out; <= 0 means dt/8).  The final accepted step ends exactly at
+ * t0+dt and its FSAL evaluation f(t0+dt, y_end) is the last RHS call, so the I_ch slots hold
+ * I_ch(y(t0+dt)).  This is the CPU twin of csrc/kem_kernel.cuh:kem_step_dp45_kernel: same
+ * formulas in the same association.
+ */
+#define DP_MAX_ATTEMPTS 100000
+
+static int dp45_row(kemo_rhs_fn rhs, int ns, double *y, double *p, double t0, double dt,
+                    double rtol, double atol, double *hsug, int64_t *n_acc, int64_t *n_rej)
+{
+    static const double c2 = 1.0 / 5.0, c3 = 3.0 / 10.0, c4 = 4.0 / 5.0, c5 = 8.0 / 9.0;
+    static const double a21 = 1.0 / 5.0;
+    static const double a31 = 3.0 / 40.0, a32 = 9.0 / 40.0;
+    static const double a41 = 44.0 / 45.0, a42 = -56.0 / 15.0, a43 = 32.0 / 9.0;
+    static const double a51 = 19372.0 / 6561.0, a52 = -25360.0 / 2187.0, a53 = 64448.0 / 6561.0,
+                        a54 = -212.0 / 729.0;
+    static const double a61 = 9017.0 / 3168.0, a62 = -355.0 / 33.0, a63 = 46732.0 / 5247.0,
+                        a64 = 49.0 / 176.0, a65 = -5103.0 / 18656.0;
+    static const double b1 = 35.0 / 384.0, b3 = 500.0 / 1113.0, b4 = 125.0 / 192.0,
+                        b5 = -2187.0 / 6784.0, b6 = 11.0 / 84.0;
+    static const double e1 = 71.0 / 57600.0, e3 = -71.0 / 16695.0, e4 = 71.0 / 1920.0,
+                        e5 = -17253.0 / 339200.0, e6 = 22.0 / 525.0, e7 = -1.0 / 40.0;
+    double k1[MAX_NS], k2[MAX_NS], k3[MAX_NS], k4[MAX_NS], k5[MAX_NS], k6[MAX_NS], k7[MAX_NS];
+    double w[MAX_NS], yn[MAX_NS];
+    const double t_end = t0 + dt;
+    double t = t0;
+    double h_try = *hsug;
+    if (!(h_try > 0.0) || !isfinite(h_try)) h_try = dt / 8.0;
+    if (h_try > dt) h_try = dt;
+    int rejected = 0;
+    rhs(t, y, k1, p);
+    for (int attempt = 0; attempt < DP_MAX_ATTEMPTS; ++attempt) {
+        double h = h_try;
+        int last = 0;
+        if (t + h * (1.0 + 1e-9) >= t_end) {
+            h = t_end - t;
+            last = 1;
+        }
+        for (int i = 0; i < ns; ++i) w[i] = y[i] + h * (a21 * k1[i]);
+        rhs(t + c2 * h, w, k2, p);
+        for (int i = 0; i < ns; ++i) w[i] = y[i] + h * (a31 * k1[i] + a32 * k2[i]);
+        rhs(t + c3 * h, w, k3, p);
+        for (int i = 0; i < ns; ++i) w[i] = y[i] + h * ((a41 * k1[i] + a42 * k2[i]) + a43 * k3[i]);
+        rhs(t + c4 * h, w, k4, p);
+        for (int i = 0; i < ns; ++i)
+            w[i] = y[i] + h * (((a51 * k1[i] + a52 * k2[i]) + a53 * k3[i]) + a54 * k4[i]);
+        rhs(t + c5 * h, w, k5, p);
+        for (int i = 0; i < ns; ++i)
+            w[i] = y[i] + h * ((((a61 * k1[i] + a62 * k2[i]) + a63 * k3[i]) + a64 * k4[i]) + a65 * k5[i]);
+        const double t_new = last ? t_end : t + h;
+        rhs(t_new, w, k6, p);
+        for (int i = 0; i < ns; ++i)
+            yn[i] = y[i] + h * ((((b1 * k1[i] + b3 * k3[i]) + b4 * k4[i]) + b5 * k5[i]) + b6 * k6[i]);
+        rhs(t_new, yn, k7, p);
+        double sum = 0.0;
+        for (int i = 0; i < ns; ++i) {
+            const double ei = h * (((((e1 * k1[i] + e3 * k3[i]) + e4 * k4[i]) + e5 * k5[i]) + e6 * k6[i])
+                                   + e7 * k7[i]);
+            const double sc = atol + rtol * fmax(fabs(y[i]), fabs(yn[i]));
+            const double r = ei / sc;
+            sum += r * r;
+        }
+        const double err = sqrt(sum / (double)ns);
+        if (err <= 1.0) {
+            double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+            if (rejected) factor = fmin(1.0, factor);
+            t = t_new;
+            for (int i = 0; i < ns; ++i) { y[i] = yn[i]; k1[i] = k7[i]; }
+            *n_acc += 1;
+            rejected = 0;
+            const double h_next = h * factor;
+            h_try = last ? fmax(h_next, h_try) : h_next;
+            if (last) {
+                *hsug = h_try > dt ? dt : h_try;
+                return 0;
+            }
+        } else {
+            const double factor = (err == err) ? fmax(0.2, 0.9 * pow(err, -0.2)) : 0.2;
+            h_try = h * factor;
+            rejected = 1;
+            *n_rej += 1;
+            if (!(h_try > 1e-14 * fabs(dt))) break;   /* step size collapsed (or NaN) */
+        }
+    }
+    *hsug = 0.0;
+    return 1;   /* failed: the reference's `assert success` */
+}
+
+int64_t kemo_step_dp45_fn(kemo_rhs_fn rhs, int ns, int np, int64_t n, double *states, double *params,
+                          double *hsug, double t0, double dt, double rtol, double atol, int n_threads,
+                          int64_t *stats /* [accepted, rejected] or NULL */)
+{
+    int64_t bad = 0, acc = 0, rej = 0;
+    if (ns > MAX_NS) return -1;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#else
+    (void)n_threads;
+#endif
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : bad, acc, rej)
+    for (int64_t r = 0; r < n; ++r) {
+        double *y = states + r * ns;
+        int64_t a = 0, j = 0;
+        int fail = dp45_row(rhs, ns, y, params + r * np, t0, dt, rtol, atol, hsug + r, &a, &j);
+        acc += a;
+        rej += j;
+        for (int i = 0; i < ns && !fail; ++i)
+            if (!isfinite(y[i])) fail = 1;
+        bad += fail;
+    }
+    if (stats) { stats[0] = acc; stats[1] = rej; }
+    return bad;
+}
+
+int64_t kemo_step_dp45(int model, int64_t n, double *states, double *params, double *hsug, double t0,
+                       double dt, double rtol, double atol, int n_threads, int64_t *stats)
+{
+    if (model < 0 || model >= N_MODELS) return -1;
+    return kemo_step_dp45_fn(MODELS[model].rhs, MODELS[model].ns, MODELS[model].np, n, states, params,
+                             hsug, t0, dt, rtol, atol, n_threads, stats);
+}
+
 int kemo_max_threads(void)
 {
 #ifdef _OPENMP

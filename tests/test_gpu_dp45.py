@@ -1,0 +1,103 @@
+"""Scheme O3: error-controlled Dormand-Prince 5(4) on the device
+against its CPU twin (oracle/knpemi_oracle.c:dp45_row) and against a tight fixed-step
+solution.  Restores what the reference's LSODA provides -- per-DOF error control at
+rtol 1e-8 / atol 1e-10 (odeSolver.py:120) -- which the fixed-step scheme O1 does not."""
+import numpy as np
+import pytest
+
+from ducks_for_tests import Space
+from workloads import SETUP, builtin, load_tables, synthetic_tables
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    scale = np.maximum(np.abs(b), 1e-3 * np.max(np.abs(b), axis=0, keepdims=True) + 1e-300)
+    return float(np.max(np.abs(a - b) / scale))
+
+
+@pytest.mark.parametrize("name", ["hh_ideal", "hh_tissue", "glial_tissue", "calibration", "hh_test"])
+def test_device_dp45_matches_cpu_twin_and_tolerance(built, name):
+    from knpemi_b200.odeSolver import MembraneModel
+    from oracle import cpu_oracle
+    n, n_steps = 20_000, 8
+    ode = builtin(name)
+    cfg = SETUP[name]
+    S, P, X, mask = synthetic_tables(name, n, seed=17)
+    gpu = MembraneModel(ode, None, 1, Space(X), verbose=False, devices=[0], scheme="dp45")
+    load_tables(gpu, S, P)
+    c_stim = ode.parameter_indices("stim_amplitude")
+    S_twin, P_twin, hs = S.copy(), P.copy(), np.zeros(n)
+    S_ref, P_ref = S.copy(), P.copy()
+    t, acc_cpu, rej_cpu = 0.0, 0, 0
+    for _ in range(n_steps):
+        gpu.step_lsoda(cfg["dt"], {"stim_amplitude": cfg["stim"]}, lambda x: x[0] < 20e-6)
+        for Pm in (P_twin, P_ref):
+            Pm[mask, c_stim] = cfg["stim"]
+        bad, a, r = cpu_oracle.step_dp45(name, S_twin, P_twin, hs, t, cfg["dt"])
+        assert bad == 0
+        acc_cpu, rej_cpu = acc_cpu + a, rej_cpu + r
+        cpu_oracle.step(name, S_ref, P_ref, t, cfg["dt"], 400)          # tight RK4 reference
+        t = t + cfg["dt"]
+    got_S, got_P = np.asarray(gpu.states), np.asarray(gpu.parameters)
+    acc_gpu, rej_gpu = gpu.step_stats()
+    gpu.close()
+    # same algorithm on both sides: identical step sequences, rounding-level differences
+    assert (acc_gpu, rej_gpu) == (acc_cpu, rej_cpu)
+    assert rel(got_S, S_twin) < 1e-10
+    assert rel(got_P, P_twin) < 1e-10
+    # and the error control delivers: within 1e-7 of the tight solution
+    assert rel(got_S, S_ref) < 1e-7
+    # fewer right-hand-side evaluations than scheme O1's 101 per DOF-step
+    rhs_per_dof_step = (6 * (acc_gpu + rej_gpu)) / (n * n_steps) + 1
+    assert rhs_per_dof_step < 80, rhs_per_dof_step
+
+
+def test_dp45_quiescent_membrane_takes_few_steps(built):
+    """A resting membrane needs one or two steps per PDE step -- the point of error control."""
+    from knpemi_b200.odeSolver import MembraneModel
+    name = "hh_ideal"
+    ode = builtin(name)
+    n = 4096
+    gpu = MembraneModel(ode, None, 1, Space(np.zeros((n, 3))), verbose=False, devices=[0], scheme="dp45")
+    cfg = SETUP[name]
+    for k, v in {**cfg["uniform"], **cfg["varying"]}.items():
+        gpu.set_parameter_values({k: lambda x, v=v: v})
+    for _ in range(10):
+        gpu.step_lsoda(1e-4, {"stim_amplitude": 0.0})
+    gpu.step_stats()
+    for _ in range(10):
+        gpu.step_lsoda(1e-4, {"stim_amplitude": 0.0})
+    acc, rej = gpu.step_stats()
+    assert acc / (n * 10) <= 2.0 and rej == 0
+    y0 = ode.init_state_values()
+    assert np.max(np.abs(np.asarray(gpu.states) - y0) / np.abs(y0)) < 1e-9      # K1 fixed point
+    gpu.close()
+
+
+def test_dp45_tolerances_and_errors(built):
+    from knpemi_b200._cabi import KemError
+    from knpemi_b200.odeSolver import MembraneModel
+    ode = builtin("hh_test")
+    with pytest.raises(ValueError, match="unknown scheme"):
+        MembraneModel(ode, None, 1, Space(np.zeros((4, 3))), verbose=False, devices=[0], scheme="bdf")
+    with pytest.raises(KemError):
+        MembraneModel(ode, None, 1, Space(np.zeros((4, 3))), verbose=False, devices=[0], scheme="dp45", rtol=-1)
+    loose = MembraneModel(ode, None, 1, Space(np.zeros((256, 3))), verbose=False, devices=[0], scheme="dp45",
+                          rtol=1e-4, atol=1e-6)
+    tight = MembraneModel(ode, None, 1, Space(np.zeros((256, 3))), verbose=False, devices=[0], scheme="dp45",
+                          rtol=1e-11, atol=1e-13)
+    for m in (loose, tight):
+        for _ in range(5):
+            m.step_lsoda(0.1, {"stim_amplitude": 0.5})
+    a_loose, _ = loose.step_stats()
+    a_tight, _ = tight.step_stats()
+    assert a_tight > 2 * a_loose
+    d = np.max(np.abs(np.asarray(loose.states) - np.asarray(tight.states)))
+    assert 1e-12 < d < 1e-2
+    bad = MembraneModel(ode, None, 1, Space(np.zeros((8, 3))), verbose=False, devices=[0], scheme="dp45")
+    bad.states[3, 3] = np.nan
+    with pytest.raises(AssertionError):
+        bad.step_lsoda(0.1, None)
+    for m in (loose, tight, bad):
+        m.close()
