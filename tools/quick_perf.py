@@ -14,13 +14,14 @@ def main():
     names = sys.argv[1].split(",") if len(sys.argv) > 1 else list(BUILTIN)
     n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 1_000_000
     blocks = [int(b) for b in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
+    scheme = sys.argv[4] if len(sys.argv) > 4 else "rk4"
     tf, ms = _cabi.fp64_peak(0)
     print(f"fp64 DFMA peak: {tf:.2f} TFLOP/s ({ms:.3f} ms/launch); hbm copy {_cabi.hbm_copy_peak(0):.0f} GB/s")
     for name in names:
         ode = BUILTIN[name]
         S, P, X, mask = synthetic_tables(name, n, seed=20240611)
         for block in blocks:
-            m = MembraneModel(ode, None, 1, PointSpace(X), devices=[0], verbose=False, block=block)
+            m = MembraneModel(ode, None, 1, PointSpace(X), devices=[0], verbose=False, block=block, scheme=scheme)
             for c in range(S.shape[1]):
                 m.states[:, c] = S[:, c]
             for c in range(P.shape[1]):
@@ -37,6 +38,10 @@ def main():
                 ts.append(m.last_step_times["ms_kernel"])
             best, med = min(ts[2:]), float(np.median(ts[2:]))
             info = m.launch_info(block)
+            if scheme == "dp45":
+                a, r = m.step_stats()
+                print(f"   dp45: {a / n / 8:.2f} accepted + {r / n / 8:.2f} rejected steps per DOF-step "
+                      f"= {6 * (a + r) / n / 8 + 1:.1f} RHS evaluations (rk4 x 25: 101)")
             print(f"{name:13s} N={n:.0e} block={block or 'def'} regs={info['registers_per_thread']} "
                   f"blk/SM={info['blocks_per_sm']} kernel {med:.3f} ms (best {best:.3f}) -> "
                   f"{n / med * 1e3:.3e} DOF-steps/s")
