@@ -842,11 +842,20 @@ int kem_set_column(kem_handle h, int kind, int col, const double *src, int64_t n
     return KEM_OK;
 }
 
-static int upload_mask_tmp(Shard &s, const uint8_t *host_mask, unsigned char **d_tmp)
+// scratch device buffer of a setter call, released on every exit path
+struct ScratchBuf {
+    void *p = nullptr;
+    ~ScratchBuf()
+    {
+        if (p) cudaFree(p);
+    }
+};
+
+static int upload_mask_tmp(Shard &s, const uint8_t *host_mask, ScratchBuf &buf)
 {
     CK(cudaSetDevice(s.dev));
-    CK(cudaMalloc(d_tmp, (size_t)s.n));
-    CK(cudaMemcpyAsync(*d_tmp, host_mask + s.begin, (size_t)s.n, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMalloc(&buf.p, (size_t)s.n));
+    CK(cudaMemcpyAsync(buf.p, host_mask + s.begin, (size_t)s.n, cudaMemcpyHostToDevice, s.stream));
     return KEM_OK;
 }
 
@@ -863,19 +872,17 @@ int kem_set_column_masked(kem_handle h, int kind, int col, const double *src,
     }
     for (Shard &s : h->shards) {
         if (s.n == 0) continue;
-        unsigned char *d_m = nullptr;
-        double *d_src = nullptr;
-        rc = upload_mask_tmp(s, host_mask, &d_m);
+        ScratchBuf d_m, d_src;
+        rc = upload_mask_tmp(s, host_mask, d_m);
         if (rc) return rc;
-        CK(cudaMalloc(&d_src, (size_t)s.n * sizeof(double)));
-        rc = copy_in(s, d_src, src + s.begin, (size_t)s.n * sizeof(double), s.stream, false);
+        CK(cudaMalloc(&d_src.p, (size_t)s.n * sizeof(double)));
+        rc = copy_in(s, (double *)d_src.p, src + s.begin, (size_t)s.n * sizeof(double), s.stream, false);
         if (rc) return rc;
-        k_copy_masked<<<grid_for(s.n), 256, 0, s.stream>>>(col_ptr(s, kind, col), d_src, d_m, s.n);
+        k_copy_masked<<<grid_for(s.n), 256, 0, s.stream>>>(col_ptr(s, kind, col), (const double *)d_src.p,
+                                                           (const unsigned char *)d_m.p, s.n);
         CK(cudaGetLastError());
         h->launches++;
         CK(cudaStreamSynchronize(s.stream));
-        CK(cudaFree(d_m));
-        CK(cudaFree(d_src));
     }
     return KEM_OK;
 }
@@ -893,14 +900,14 @@ int kem_set_value_masked(kem_handle h, int kind, int col, double v, const uint8_
     }
     for (Shard &s : h->shards) {
         if (s.n == 0) continue;
-        unsigned char *d_m = nullptr;
-        rc = upload_mask_tmp(s, host_mask, &d_m);
+        ScratchBuf d_m;
+        rc = upload_mask_tmp(s, host_mask, d_m);
         if (rc) return rc;
-        k_set_value_masked<<<grid_for(s.n), 256, 0, s.stream>>>(col_ptr(s, kind, col), d_m, s.n, v);
+        k_set_value_masked<<<grid_for(s.n), 256, 0, s.stream>>>(col_ptr(s, kind, col),
+                                                                (const unsigned char *)d_m.p, s.n, v);
         CK(cudaGetLastError());
         h->launches++;
         CK(cudaStreamSynchronize(s.stream));
-        CK(cudaFree(d_m));
     }
     return KEM_OK;
 }
