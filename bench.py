@@ -163,6 +163,16 @@ class Dist:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t.item())
 
+    def gather(self, x: float) -> list:
+        """Value of every rank (sum-reduction of one-hot vectors)."""
+        if self.world == 1:
+            return [x]
+        dev = "cuda" if self.backend == "nccl" else "cpu"
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device=dev)
+        t[self.rank] = x
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
     def close(self):
         if self.world > 1:
             self.dist.destroy_process_group()
@@ -305,6 +315,11 @@ def run_gpu(args, dist: Dist):
     dev = dist.local_rank
     if _cabi.device_count() <= dev:
         raise SystemExit("bench.py: no CUDA device for this rank -- the product has no CPU path")
+    # several ranks on a multi-socket host: keep this rank's pinned buffers next to its GPU
+    cpus = []
+    if dist.world > 1 and not os.environ.get("KNPEMI_NO_AFFINITY"):
+        from knpemi_b200.affinity import bind_to_device
+        cpus = bind_to_device(dev)
 
     S, P, X, mask = synthetic_tables(model_name, n, seed=20240611 + dist.rank)
     model = MembraneModel(ode, None, 1, PointSpace(X), devices=[dev], verbose=False, n_sub=N_SUB,
@@ -371,6 +386,8 @@ def run_gpu(args, dist: Dist):
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     dist.barrier()
     e2e_ms_max = dist.max(e2e_wall_ms)
+    e2e_per_rank = [round(v / e2e_steps, 3) for v in dist.gather(e2e_wall_ms)]
+    e2e_dev_per_rank = [round(v / e2e_steps, 3) for v in dist.gather(dev_ms)]
     e2e_value = total_dofs * e2e_steps / (e2e_ms_max * 1e-3)
     last = dict(model.last_step_times)
 
@@ -461,11 +478,13 @@ def run_gpu(args, dist: Dist):
                        "l2": f"inputs {ALGO_BYTES[model_name] * n / 1e6:.0f} MB per GPU "
                              f"{'>' if ALGO_BYTES[model_name] * n > 126e6 else '<'} 126 MB L2, no flush",
                        "parallelism": f"{dist.world} x contiguous DOF ranges, no collective",
+                       "rank0_cpu_affinity": f"{len(cpus)} CPUs local to GPU {dev}" if cpus else "unchanged",
                        "block": args.block or 128, "registers_per_thread": info["registers_per_thread"],
                        "blocks_per_sm": info["blocks_per_sm"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d * dist.world),
                     "d2h_bytes_per_step": int(d2h * dist.world), "steps": e2e_steps,
                     "ms_per_step_wall": e2e_ms_max / e2e_steps, "ms_per_step_device": dev_ms / e2e_steps,
+                    "ms_per_step_wall_per_rank": e2e_per_rank, "ms_per_step_device_per_rank": e2e_dev_per_rank,
                     "last_step_ms": last,
                     "api": "MembraneModel.step_exchange (kem_step_io): 7 input columns from pinned host "
                            "memory, fused step, 4 output columns back, chunk-pipelined",

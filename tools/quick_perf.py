@@ -15,13 +15,14 @@ def main():
     n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 1_000_000
     blocks = [int(b) for b in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
     scheme = sys.argv[4] if len(sys.argv) > 4 else "rk4"
+    nvcc_flags = tuple(sys.argv[5].split()) if len(sys.argv) > 5 else ()
     tf, ms = _cabi.fp64_peak(0)
     print(f"fp64 DFMA peak: {tf:.2f} TFLOP/s ({ms:.3f} ms/launch); hbm copy {_cabi.hbm_copy_peak(0):.0f} GB/s")
     for name in names:
         ode = BUILTIN[name]
         S, P, X, mask = synthetic_tables(name, n, seed=20240611)
         for block in blocks:
-            m = MembraneModel(ode, None, 1, PointSpace(X), devices=[0], verbose=False, block=block, scheme=scheme)
+            m = MembraneModel(ode, None, 1, PointSpace(X), devices=[0], verbose=False, block=block, scheme=scheme, nvcc_flags=nvcc_flags)
             for c in range(S.shape[1]):
                 m.states[:, c] = S[:, c]
             for c in range(P.shape[1]):
