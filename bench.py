@@ -196,11 +196,19 @@ def fp64_slots(model_name: str, n_sub: int):
     return float(4 * n_sub * e["loop_fp64"] + e["once_fp64"]), "sass-static"
 
 
+def host_threads() -> int:
+    """Every core this process may use -- not OMP_NUM_THREADS, which torchrun sets to 1."""
+    try:
+        return max(len(os.sched_getaffinity(0)), 1)
+    except AttributeError:
+        return max(os.cpu_count() or 1, 1)
+
+
 def run_cpu_oracle(model_name: str, target_seconds: float, seed: int):
     """Oracle port of the reference stepping on the host cores: (DOF-steps/s, threads, sample)."""
     from oracle import cpu_oracle
     from workloads import SETUP, synthetic_tables
-    threads = cpu_oracle.max_threads()
+    threads = host_threads()
     cfg = SETUP[model_name]
     c_probe = 4000 * max(threads, 1)
     S, P, X, mask = synthetic_tables(model_name, c_probe, seed)
@@ -262,7 +270,7 @@ def run_reference(args, dist: Dist):
     from workloads import SETUP, synthetic_tables
     model_name, n_per_gpu, cfg_text = WORKLOADS[args.workload]
     cfg = SETUP[model_name]
-    threads = cpu_oracle.max_threads()
+    threads = host_threads()
     probe_n = 4000 * max(threads, 1)
     S, P, X, mask = synthetic_tables(model_name, probe_n, 20240611)
     t0 = time.perf_counter()

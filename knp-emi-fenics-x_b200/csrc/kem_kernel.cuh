@@ -71,8 +71,15 @@ __device__ __forceinline__ void kem_prologue(const KemArgs<M> &a, long long i, t
     M::hoist(p, q);
 }
 
+// KEM_MIN_BLOCKS (compile-time, default 1) is the minimum-resident-blocks hint of
+// __launch_bounds__ for the RK4 kernel: a register cap for occupancy experiments
+// (`nvcc_flags=("-DKEM_MIN_BLOCKS=8",)`); the measured optimum is the uncapped default.
+#ifndef KEM_MIN_BLOCKS
+#define KEM_MIN_BLOCKS 1
+#endif
+
 template <class M, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, KEM_MIN_BLOCKS)
 kem_step_kernel(const __grid_constant__ KemArgs<M> a)
 {
     constexpr int NS = M::NS, NOUT = M::NOUT, NT = M::NT;
