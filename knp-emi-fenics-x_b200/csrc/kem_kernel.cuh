@@ -20,6 +20,7 @@
 // Binding roofline: the FP64 pipe (about 25k DFMA-class instructions against
 // 144 bytes per DOF-step for the HH models) -- see DESIGN.md.
 #pragma once
+#include "kem_math.cuh"
 #include "kem_model_api.h"
 
 template <class M>
@@ -251,9 +252,12 @@ kem_step_dp45_kernel(const __grid_constant__ KemArgs<M> a)
             const double r = ei / sc;
             sum += r * r;
         }
-        const double err = sqrt(sum / (double)NS);
-        if (err <= 1.0) {
-            double factor = (err == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+        // err = sqrt(err2); the twin tests err <= 1, which is err2 <= 1 exactly (sqrt is monotone
+        // and sqrt(1) = 1), and 0.9 err^(-1/5) = 0.9 exp(-0.1 log err2): no sqrt, no libm pow
+        const double err2 = sum / (double)NS;
+        const double shrink = 0.9 * kem::exp(-0.1 * kem::log(err2));
+        if (err2 <= 1.0) {
+            double factor = (err2 == 0.0) ? 10.0 : fmin(10.0, shrink);
             if (rejected) factor = fmin(1.0, factor);
             t = t_new;
 #pragma unroll
@@ -267,7 +271,7 @@ kem_step_dp45_kernel(const __grid_constant__ KemArgs<M> a)
                 break;
             }
         } else {
-            const double factor = (err == err) ? fmax(0.2, 0.9 * pow(err, -0.2)) : 0.2;
+            const double factor = (err2 == err2) ? fmax(0.2, shrink) : 0.2;
             h_try = h * factor;
             rejected = true;
             ++n_rej;

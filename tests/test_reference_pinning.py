@@ -17,8 +17,6 @@ P = ctypes.POINTER(ctypes.c_double)
 
 
 def _points(ref, name, n, seed):
-    import importlib
-    mk = importlib.import_module("golden.make_golden") if False else None  # noqa: F841
     from workloads import SETUP
     rng = np.random.default_rng(seed)
     y0, p0 = ref.init_state_values(), ref.init_parameter_values()

@@ -50,7 +50,6 @@ def main():
 
 def _pname(ode, c):
     # reverse lookup of a parameter name from its column
-    import inspect
     for nm, _ in getattr(ode, "PARAMETERS"):
         if ode.parameter_indices(nm) == c:
             return nm
