@@ -106,3 +106,48 @@ def test_config4_two_tags_side_by_side(built):
         assert close(np.asarray(g.states), c.states)
         assert close(np.asarray(g.parameters), c.parameters)
         g.close()
+
+
+def test_config4_scale_1e8_dofs_in_eight_ranges(built):
+    """configs[4] scale: 10^8 membrane DOFs split into eight contiguous ranges (here eight shards
+    of one device; on an 8 x B200 box the same handle spans the eight GPUs).  No oracle can run at
+    this size, so the check is a size-independent property: DOFs are independent, hence 10^8
+    identical DOFs must all end bitwise equal to the same DOF stepped in a 1000-DOF model."""
+    from knpemi_b200.odeSolver import MembraneModel
+    name = "hh_tissue"
+    ode = builtin(name)
+    cfg = SETUP[name]
+    n_big = 100_000_000
+
+    def run(n, devices):
+        X = np.broadcast_to(np.zeros((1, 3)), (n, 3))          # no 2.4 GB coordinate table
+        m = MembraneModel(ode, None, 1, Space(X) if n < 10_000 else _BroadcastSpace(n), verbose=False,
+                          devices=devices)
+        for k, v in {**cfg["uniform"], **cfg["varying"]}.items():
+            m.set_parameter_values({k: lambda x, v=v: v})
+        for _ in range(2):
+            m.step_lsoda(0.1, {'stim_amplitude': 5.0})
+        return m
+
+    small = run(1000, [0])
+    want_S, want_P = np.asarray(small.states)[0], np.asarray(small.parameters)[0]
+    small.close()
+    big = run(n_big, [0] * 8)
+    assert big.states.shape == (n_big, 4)
+    for c in range(4):
+        col = big.states[:, c]
+        assert col[0] == want_S[c] and np.all(col == col[0])
+    for c in (15, 16, 17):
+        col = big.parameters[:, c]
+        assert col[0] == want_P[c] and np.all(col == col[0])
+    big.close()
+
+
+class _BroadcastSpace:
+    """N identical DOF coordinates without materialising them."""
+
+    def __init__(self, n):
+        self._x = np.broadcast_to(np.zeros((1, 3)), (n, 3))
+
+    def tabulate_dof_coordinates(self):
+        return self._x
