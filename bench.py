@@ -331,7 +331,7 @@ def run_gpu(args, dist: Dist):
 
     S, P, X, mask = synthetic_tables(model_name, n, seed=20240611 + dist.rank)
     model = MembraneModel(ode, None, 1, PointSpace(X), devices=[dev], verbose=False, n_sub=N_SUB,
-                          block=args.block)
+                          block=args.block, scheme=args.scheme)
     load_tables(model, S, P)
     stim = {"stim_amplitude": cfg["stim"]}
     locator = lambda x: x[0] < 20e-6                 # noqa: E731  (run_2D.py:264)
@@ -357,6 +357,15 @@ def run_gpu(args, dist: Dist):
     dist.barrier()
     launches = model.launch_count() - launches0
     clocks = sampler.stop(wall0, wall1)
+    dp45_steps = None
+    if args.scheme == "dp45":
+        model.step_stats()                                   # discard warm-up counts
+        for _ in range(3):
+            model.step_async(dt, stim, locator)
+        acc, rej = model.step_stats()
+        dp45_steps = {"accepted_per_dof_step": acc / (3.0 * n), "rejected_per_dof_step": rej / (3.0 * n),
+                      "rhs_evals_per_dof_step": 6.0 * (acc + rej) / (3.0 * n) + 1.0,
+                      "rtol": model.rtol, "atol": model.atol}
     ms_max = dist.max(ms)
     total_dofs = dist.sum(float(n))
     value = total_dofs * args.steps / (ms_max * 1e-3)
@@ -431,6 +440,11 @@ def run_gpu(args, dist: Dist):
     # ------------------------------------------------ roofline of the fused kernel
     peak_tf, _ = _cabi.fp64_peak(dev)
     slots, slots_src = fp64_slots(model_name, N_SUB)
+    if dp45_steps and slots:
+        # O3 spends a data-dependent number of RHS evaluations: scale the per-RHS count of the
+        # O1 kernel (same generated right-hand side) by the measured evaluations per DOF-step
+        slots = slots / (4 * N_SUB + 1) * dp45_steps["rhs_evals_per_dof_step"]
+        slots_src += " x measured RHS evaluations of scheme O3 (excludes controller arithmetic)"
     kernel_ms = ms / args.steps                       # this rank's average launch duration
     roofline = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak_tf,
                 "peak_source": "measured in this run: kem_fp64_peak (8 independent DFMA chains/thread, "
@@ -481,8 +495,10 @@ def run_gpu(args, dist: Dist):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "model": model_name, "baseline_config": cfg_text,
-                       "dofs_per_gpu": n, "scheme": "rk4", "n_sub": N_SUB, "dt": dt,
-                       "rhs_evals_per_dof_step": 4 * N_SUB + 1, "stimulus": "masked, x[0] < 20e-6 (~32 % of DOFs)",
+                       "dofs_per_gpu": n, "scheme": args.scheme, "n_sub": N_SUB if args.scheme == "rk4" else None,
+                       "dt": dt, "dp45": dp45_steps,
+                       "rhs_evals_per_dof_step": 4 * N_SUB + 1 if args.scheme == "rk4"
+                       else dp45_steps["rhs_evals_per_dof_step"], "stimulus": "masked, x[0] < 20e-6 (~32 % of DOFs)",
                        "l2": f"inputs {ALGO_BYTES[model_name] * n / 1e6:.0f} MB per GPU "
                              f"{'>' if ALGO_BYTES[model_name] * n > 126e6 else '<'} 126 MB L2, no flush",
                        "parallelism": f"{dist.world} x contiguous DOF ranges, no collective",
@@ -500,7 +516,8 @@ def run_gpu(args, dist: Dist):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
-            "rhs_evals_per_s": value * (4 * N_SUB + 1),
+            "rhs_evals_per_s": value * (4 * N_SUB + 1 if args.scheme == "rk4"
+                                        else dp45_steps["rhs_evals_per_dof_step"]),
         }
         if cpu:
             line["cpu_baseline"] = cpu
@@ -516,6 +533,8 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="hh_ideal_1e7")
     ap.add_argument("--dofs", type=float, default=0, help="override DOFs per GPU")
     ap.add_argument("--block", type=int, default=0, choices=[0, 64, 128, 256])
+    ap.add_argument("--scheme", choices=["rk4", "dp45"], default="rk4",
+                    help="rk4 = scheme O1 (the benchmark's normative scheme); dp45 = error-controlled O3")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -24,7 +24,8 @@ for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "bench_*.json"))):
                      d["value"], None, None, None, None))
         continue
     r = d["roofline"]
-    rows.append((d["config"]["workload"], "b200", d["n_gpus"], d["value"], d["ms_per_step"], d["e2e"]["value"],
+    rows.append((d["config"]["workload"], "b200 " + d["config"].get("scheme", "rk4"), d["n_gpus"], d["value"],
+                 d["ms_per_step"], d["e2e"]["value"],
                  r.get("frac"), r["hbm"]["frac"]))
 
 with open(out, "w") as f:
