@@ -371,3 +371,23 @@ def test_user_model_is_generated_and_compiled_at_run_time(built, tmp_path):
     cur = y[:, 0] - y[:, 0] ** 3 / 3 - y[:, 1]
     assert np.max(np.abs(m.parameters[:, 4] - cur)) < 1e-12
     m.close()
+
+
+def test_large_sub_step_counts_and_their_limit(built):
+    """The host-evaluated time table lives in shared memory: (2 n_sub + 2) * NT doubles.  Above
+    48 KB the launcher opts in to a larger carve-out; beyond 200 KB it refuses loudly."""
+    from knpemi_b200._cabi import KemError
+    from knpemi_b200.odeSolver import MembraneModel
+    from oracle import cpu_oracle
+    name = "hh_tissue"
+    S, P, X, mask = synthetic_tables(name, 257, seed=6)
+    m = MembraneModel(builtin(name), None, 1, Space(X), verbose=False, devices=[0], n_sub=4000)   # 125 KB
+    load_tables(m, S, P)
+    m.step_lsoda(0.1, None)
+    cpu_oracle.step(name, S, P, 0.0, 0.1, 4000)
+    assert close(np.asarray(m.states), S)
+    with pytest.raises(KemError):
+        m.step(0.1, None, n_sub=20000)                     # 625 KB of time table
+    with pytest.raises(KemError):
+        m.step(0.1, None, n_sub=0)
+    m.close()
