@@ -155,29 +155,38 @@ def ptr(a: np.ndarray) -> int:
     return a.ctypes.data
 
 
+def _free_pinned(ptr: int):
+    try:
+        lib().kem_host_free(C.c_void_p(ptr))
+    except Exception:
+        pass
+
+
+def pinned_empty(n: int, dtype=np.float64) -> np.ndarray:
+    """1-D NumPy array over page-locked host memory (kem_host_alloc).
+
+    The memory belongs to the array: it is released when the array (and every view of it)
+    is garbage collected, so `pinned_empty(n)` is as safe to pass around as `np.empty(n)`."""
+    import weakref
+    dtype = np.dtype(dtype)
+    nbytes = max(int(n) * dtype.itemsize, 8)
+    p = C.c_void_p()
+    check(lib().kem_host_alloc(C.byref(p), nbytes), "kem_host_alloc")
+    buf = (C.c_char * nbytes).from_address(p.value)
+    weakref.finalize(buf, _free_pinned, p.value)       # the array's base keeps `buf` alive
+    return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+
 class PinnedArray:
-    """1-D float64 / uint8 NumPy view over page-locked memory from kem_host_alloc."""
+    """Thin holder kept for callers that want an explicit object: `.array` is `pinned_empty(n)`."""
 
     def __init__(self, n: int, dtype=np.float64):
-        self.dtype = np.dtype(dtype)
-        self.nbytes = max(int(n) * self.dtype.itemsize, 8)
-        p = C.c_void_p()
-        check(lib().kem_host_alloc(C.byref(p), self.nbytes), "kem_host_alloc")
-        self._ptr = p.value
-        buf = (C.c_char * self.nbytes).from_address(self._ptr)
-        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(n))
+        self.array = pinned_empty(n, dtype)
+        self.dtype = self.array.dtype
+        self.nbytes = self.array.nbytes
 
     def free(self):
-        if self._ptr:
-            self.array = None
-            lib().kem_host_free(C.c_void_p(self._ptr))
-            self._ptr = None
-
-    def __del__(self):
-        try:
-            self.free()
-        except Exception:
-            pass
+        self.array = None
 
 
 def fp64_peak(dev: int = 0) -> tuple[float, float]:
