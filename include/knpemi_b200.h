@@ -133,6 +133,9 @@ int kem_sync(kem_handle h);
 /* tolerances of KEM_SCHEME_DP45; defaults are the reference's rtol 1e-8, atol 1e-10
  * (odeSolver.py:120) */
 int kem_set_tolerances(kem_handle h, double rtol, double atol);
+/* KEM_SCHEME_DP45 runs the DOFs in an order sorted by the step size each used last time, so
+ * that a warp's lanes finish together (default on; results do not depend on it) */
+int kem_set_activity_sort(kem_handle h, int enabled);
 /* accepted / rejected DP45 steps summed over all DOFs since the last call (waits for the
  * device); RHS evaluations = 6 * (accepted + rejected) + 1 per DOF-step */
 int kem_get_step_stats(kem_handle h, uint64_t *accepted_out, uint64_t *rejected_out);

@@ -11,7 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define KEM_MODEL_ABI_VERSION 4
+#define KEM_MODEL_ABI_VERSION 5
 #define KEM_MAX_STIM 4
 
 extern "C" {
@@ -40,6 +40,8 @@ typedef struct KemLaunch {
     double rtol, atol;              // O3: error tolerances
     double *hsug;                   // O3: per-DOF warm-start step size (read + written)
     unsigned long long *stats;      // O3: device counters [accepted steps, rejected steps]
+    const int *perm;                // O3: thread -> DOF permutation grouping DOFs of similar
+                                    //     activity into the same warps (NULL = identity)
 } KemLaunch;
 
 typedef struct KemModelDesc {

@@ -10,6 +10,7 @@
 #include "kem_copy_pool.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges cost nothing unless a tool is attached
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
@@ -49,6 +50,13 @@ int fail(int code, const std::string &msg)
     do {                                                                                 \
         if (!(cond)) return fail(KEM_E_ARG, std::string(__func__) + ": " + (msg));       \
     } while (0)
+
+// NVTX range covering one C-ABI call (the counterpart of the reference's
+// dolfinx.common.Timer('ODE step LSODA'), odeSolver.py:104)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ------------------------------------------------------------------ utility kernels
 __global__ void k_fill(double *__restrict__ dst, long long n, double v)
@@ -108,6 +116,64 @@ __global__ void k_gather_diff(double *__restrict__ dst, const double *__restrict
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) dst[i] = a[map_a[i]] - b[map_b[i]];
+}
+
+// ---- activity sort for scheme O3 (error-controlled stepping) ---------------------------
+// bucket = quarter-octaves of dt/hsug (about the number of steps the DOF took last time),
+// 0 for a DOF that has no history; 64 buckets cover up to 2^16 steps per PDE step.
+constexpr int ACT_BUCKETS = 64;
+
+__device__ __forceinline__ int activity_bucket(double hsug, double dt)
+{
+    if (!(hsug > 0.0) || !(hsug < dt)) return 0;
+    const int b = (int)(4.0 * log2(dt / hsug) + 0.5);
+    return b < 0 ? 0 : (b >= ACT_BUCKETS ? ACT_BUCKETS - 1 : b);
+}
+
+__global__ void k_activity_hist(const double *__restrict__ hsug, double dt, long long n,
+                                unsigned *__restrict__ counts)
+{
+    __shared__ unsigned s_cnt[ACT_BUCKETS];
+    for (int k = threadIdx.x; k < ACT_BUCKETS; k += blockDim.x) s_cnt[k] = 0;
+    __syncthreads();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) atomicAdd(&s_cnt[activity_bucket(hsug[i], dt)], 1u);
+    __syncthreads();
+    for (int k = threadIdx.x; k < ACT_BUCKETS; k += blockDim.x)
+        if (s_cnt[k]) atomicAdd(&counts[k], s_cnt[k]);
+}
+
+// exclusive scan of the bucket counts -> running cursors; most active bucket first, so the
+// long-running warps start early and the short ones fill the tail of the launch
+__global__ void k_activity_scan(const unsigned *__restrict__ counts, unsigned *__restrict__ cursor)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned run = 0;
+        for (int k = ACT_BUCKETS - 1; k >= 0; --k) {
+            cursor[k] = run;
+            run += counts[k];
+        }
+    }
+}
+
+__global__ void k_activity_scatter(const double *__restrict__ hsug, double dt, long long n,
+                                   unsigned *__restrict__ cursor, int *__restrict__ perm)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int b = activity_bucket(hsug[i], dt);
+        // one atomic per (warp, bucket): lanes with the same bucket share a reservation
+        const unsigned active = __activemask();
+        const unsigned peers = __match_any_sync(active, b);
+        const int leader = __ffs(peers) - 1;
+        const int lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(&cursor[b], (unsigned)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        perm[base + __popc(peers & ((1u << lane) - 1u))] = (int)i;
+    }
 }
 
 // FP64 pipe peak: 8 independent DFMA chains per thread, nothing else in the loop.
@@ -189,6 +255,9 @@ struct Shard {
     std::vector<cudaEvent_t> io_in, io_k0, io_k1, io_out;
     // scheme O3: per-DOF warm-start step size, device counters [accepted, rejected]
     double *d_hsug = nullptr;
+    int *d_perm = nullptr;                   // activity-sorted thread -> DOF map
+    unsigned *d_act = nullptr;               // [2 * ACT_BUCKETS] counts, cursors
+    bool perm_valid = false;
     unsigned long long *d_stats = nullptr;
     unsigned long long *h_stats = nullptr;   // pinned
     // membrane-DOF -> bulk-DOF maps of the device-resident exchange (f1/f3)
@@ -208,6 +277,7 @@ struct kem_handle_s {
     int block = 0;
     int64_t launches = 0;
     double rtol = 1.0e-8, atol = 1.0e-10;   // odeSolver.py:120
+    bool activity_sort = true;              // scheme O3: group DOFs of similar activity into warps
 };
 
 namespace {
@@ -423,6 +493,8 @@ int prepare_step(kem_handle h, double t0, double dt, int n_sub, int scheme, int 
             CK(cudaMalloc(&s.d_stats, 2 * sizeof(unsigned long long)));
             CK(cudaMemsetAsync(s.d_stats, 0, 2 * sizeof(unsigned long long), s.stream));
             CK(cudaHostAlloc((void **)&s.h_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+            CK(cudaMalloc(&s.d_perm, std::max<size_t>((size_t)s.n, 1) * sizeof(int)));
+            CK(cudaMalloc(&s.d_act, 2 * ACT_BUCKETS * sizeof(unsigned)));
         }
     pl.masked = !h->shards.empty() && h->shards[0].has_mask;
     for (int s = 0; s < n_stim; ++s) {
@@ -461,6 +533,25 @@ int prepare_step(kem_handle h, double t0, double dt, int n_sub, int scheme, int 
         }
     }
     h->uni_dirty = false;
+    return KEM_OK;
+}
+
+// scheme O3: counting sort of the shard's DOFs by the step size they used last time
+int build_activity_perm(kem_handle h, Shard &s, double dt)
+{
+    if (s.n == 0 || s.n > 0x7fffffffLL) {
+        s.perm_valid = false;
+        return KEM_OK;
+    }
+    CK(cudaSetDevice(s.dev));
+    CK(cudaMemsetAsync(s.d_act, 0, 2 * ACT_BUCKETS * sizeof(unsigned), s.stream));
+    k_activity_hist<<<grid_for(s.n), 256, 0, s.stream>>>(s.d_hsug, dt, s.n, s.d_act);
+    k_activity_scan<<<1, 32, 0, s.stream>>>(s.d_act, s.d_act + ACT_BUCKETS);
+    k_activity_scatter<<<grid_for(s.n), 256, 0, s.stream>>>(s.d_hsug, dt, s.n, s.d_act + ACT_BUCKETS,
+                                                            s.d_perm);
+    CK(cudaGetLastError());
+    h->launches += 3;
+    s.perm_valid = true;
     return KEM_OK;
 }
 
@@ -510,6 +601,12 @@ int launch_range(kem_handle h, Shard &s, const StepPlan &pl, int64_t off, int64_
     L.atol = h->atol;
     L.hsug = s.d_hsug ? s.d_hsug + off : nullptr;
     L.stats = s.d_stats;
+    L.perm = nullptr;
+    if (pl.scheme == KEM_SCHEME_DP45 && h->activity_sort && off == 0 && len == s.n) {
+        int rc = build_activity_perm(h, s, pl.dt);     // whole-range launches only (not the chunks
+        if (rc) return rc;                             // of kem_step_io)
+        if (s.perm_valid) L.perm = s.d_perm;
+    }
     CK(cudaSetDevice(s.dev));
     cudaError_t e = m->launch(&L, s.stream);
     if (e != cudaSuccess)
@@ -640,6 +737,7 @@ int kem_model_launch_info(int model_id, int dev, int block, int *regs_out, int *
 int kem_create(int model_id, int64_t n_dof, int n_dev, const int *dev_ids,
                const double *state_defaults, const double *param_defaults, kem_handle *out)
 {
+    NvtxRange nvtx_range("kem_create");
     ARG(out, "null output");
     *out = nullptr;
     const KemModelDesc *m = model_desc(model_id);
@@ -746,6 +844,8 @@ int kem_destroy(kem_handle h)
         if (s.d_ttab) cudaFree(s.d_ttab);
         if (s.d_flags) cudaFree(s.d_flags);
         if (s.d_hsug) cudaFree(s.d_hsug);
+        if (s.d_perm) cudaFree(s.d_perm);
+        if (s.d_act) cudaFree(s.d_act);
         if (s.d_stats) cudaFree(s.d_stats);
         if (s.h_stats) cudaFreeHost(s.h_stats);
         for (long long *m : s.d_map) if (m) cudaFree(m);
@@ -816,6 +916,7 @@ int kem_set_uniform(kem_handle h, int kind, int col, double v)
 
 int kem_set_column(kem_handle h, int kind, int col, const double *src, int64_t n)
 {
+    NvtxRange nvtx_range("kem_set_column");
     int rc = check_col(h, kind, col, __func__);
     if (rc) return rc;
     ARG(n == h->n, "length must equal the handle's n_dof");
@@ -914,6 +1015,7 @@ int kem_set_value_masked(kem_handle h, int kind, int col, double v, const uint8_
 
 int kem_get_column(kem_handle h, int kind, int col, double *dst, int64_t n)
 {
+    NvtxRange nvtx_range("kem_get_column");
     int rc = check_col(h, kind, col, __func__);
     if (rc) return rc;
     ARG(n == h->n, "length must equal the handle's n_dof");
@@ -971,6 +1073,7 @@ int kem_step_timed(kem_handle h, double t0, double dt, int n_sub, int scheme, in
                    const int *stim_cols, const double *stim_vals, int *status_flags,
                    kem_step_times *times)
 {
+    NvtxRange nvtx_range("kem_step_timed");
     StepPlan pl;
     int rc = prepare_step(h, t0, dt, n_sub, scheme, n_stim, stim_cols, stim_vals, pl);
     if (rc) return rc;
@@ -1009,6 +1112,7 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
                 const int *stim_cols, const double *stim_vals, int n_in, const kem_io_column *in,
                 int n_out, const kem_io_column *out, int *status_flags, kem_step_times *times)
 {
+    NvtxRange nvtx_range("kem_step_io");
     ARG(h, "null handle");
     ARG(n_in >= 0 && n_out >= 0 && (in || !n_in) && (out || !n_out), "bad io arrays");
     int rc;
@@ -1154,6 +1258,13 @@ int kem_sync(kem_handle h)
     if (rc) return rc;
     int flags = 0;
     return read_flags(h, &flags);
+}
+
+int kem_set_activity_sort(kem_handle h, int enabled)
+{
+    ARG(h, "null handle");
+    h->activity_sort = enabled != 0;
+    return KEM_OK;
 }
 
 int kem_set_tolerances(kem_handle h, double rtol, double atol)

@@ -79,6 +79,7 @@ SIGNATURES = {
                               _IP, C.POINTER(kem_step_times)]),
     "kem_sync": (C.c_int, [_H]),
     "kem_set_tolerances": (C.c_int, [_H, C.c_double, C.c_double]),
+    "kem_set_activity_sort": (C.c_int, [_H, C.c_int]),
     "kem_get_step_stats": (C.c_int, [_H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "kem_timer_begin": (C.c_int, [_H]),
     "kem_timer_end": (C.c_int, [_H, _DP]),

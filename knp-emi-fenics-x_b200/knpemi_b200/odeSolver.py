@@ -379,6 +379,10 @@ class MembraneModel:
         check(self._lib.kem_timer_end(self._h, C.byref(ms)), "kem_timer_end")
         return ms.value
 
+    def set_activity_sort(self, enabled=True):
+        '''Scheme "dp45": run DOFs sorted by the step size they used last (default on).'''
+        check(self._lib.kem_set_activity_sort(self._h, int(bool(enabled))), "kem_set_activity_sort")
+
     def step_stats(self):
         '''(accepted, rejected) DP45 steps over all DOFs since the last call.'''
         a, r = C.c_uint64(0), C.c_uint64(0)

@@ -111,3 +111,21 @@ def test_dp45_tolerances_and_errors(built):
         bad.step_lsoda(0.1, None)
     for m in (loose, tight, bad):
         m.close()
+
+
+def test_activity_sorted_execution_does_not_change_results(built):
+    """The thread -> DOF permutation only decides which lanes share a warp: bitwise same tables."""
+    from knpemi_b200.odeSolver import MembraneModel
+    name, n = "hh_tissue", 100_003
+    S, P, X, mask = synthetic_tables(name, n, seed=23)
+    res = []
+    for sort in (True, False):
+        m = MembraneModel(builtin(name), None, 1, Space(X), verbose=False, devices=[0, 0], scheme="dp45")
+        m.set_activity_sort(sort)
+        load_tables(m, S, P)
+        for _ in range(4):
+            m.step_lsoda(0.1, {"stim_amplitude": 5.0}, lambda x: x[0] < 20e-6)
+        res.append((np.asarray(m.states), np.asarray(m.parameters), m.step_stats()))
+        m.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert res[0][2] == res[1][2]

@@ -30,6 +30,8 @@ def main():
                     m.set_parameter_values({_pname(ode, c): (lambda x, v=P[0, c]: v)})
                 else:
                     m._set_column(1, c, np.ascontiguousarray(P[:, c]))
+            if os.environ.get("KNPEMI_NO_ACTIVITY_SORT"):
+                m.set_activity_sort(False)
             dt = SETUP[name]["dt"]
             stim = {"stim_amplitude": SETUP[name]["stim"]}
             loc = lambda x: x[0] < 20e-6
