@@ -141,3 +141,12 @@ def test_model_without_source_file_is_refused():
             return np.zeros(1)
     with pytest.raises(ModelSourceError, match="__file__"):
         codegen.generate(Fake)
+
+
+@pytest.mark.parametrize("name", ["hh_ideal", "calibration"])
+def test_committed_sample_of_generated_code_is_current(name):
+    """docs/generated_<model>.cu is what the generator emits today (kept for readers who want
+    to see the device code without running anything)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "docs", f"generated_{name}.cu")) as f:
+        assert f.read() == codegen.generate(builtin(name)).source
