@@ -1,4 +1,5 @@
-"""Per-column error report of the CUDA kernel against the oracle (development tool)."""
+"""Per-column error report of the CUDA kernel against the oracle (test infrastructure: it uses
+the oracle, so it lives under tests/).  Usage: python tests/diag_parity.py <model> <n> <steps>"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "tests"), os.path.join(ROOT, "knp-emi-fenics-x_b200"), ROOT]
