@@ -44,6 +44,7 @@ struct KemArgs {
     double *hsug;
     unsigned long long *stats;
     const int *perm;
+    const unsigned *perm_on;
 };
 
 // Prologue shared by the step kernels: parameters of DOF i (only the slots the RHS
@@ -179,7 +180,7 @@ kem_step_dp45_kernel(const __grid_constant__ KemArgs<M> a)
     // counts last time, so a warp is not held up by one active lane (kem_runtime.cu:
     // build_activity_perm).  The loads and stores below become sector-granular gathers;
     // at 2 % of HBM bandwidth that is free.
-    const long long i = a.perm ? (long long)a.perm[tid] : tid;
+    const long long i = (a.perm && a.perm_on[0]) ? (long long)a.perm[tid] : tid;
 
     typename M::H q;
     kem_prologue<M>(a, i, q);
@@ -360,7 +361,7 @@ static cudaError_t kem_launch(const KemLaunch *L, cudaStream_t stream)
     a.h = L->h;
     a.flags = L->flags;
     a.t0 = L->t0; a.dt = L->dt; a.t_end = L->t_end; a.rtol = L->rtol; a.atol = L->atol;
-    a.hsug = L->hsug; a.stats = L->stats; a.perm = L->perm;
+    a.hsug = L->hsug; a.stats = L->stats; a.perm = L->perm; a.perm_on = L->perm_on;
     if (L->scheme == 1) {
         const int blk = L->block ? L->block : M::DEFAULT_BLOCK;
         switch (blk) {

@@ -11,7 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define KEM_MODEL_ABI_VERSION 5
+#define KEM_MODEL_ABI_VERSION 6
 #define KEM_MAX_STIM 4
 
 extern "C" {
@@ -42,6 +42,7 @@ typedef struct KemLaunch {
     unsigned long long *stats;      // O3: device counters [accepted steps, rejected steps]
     const int *perm;                // O3: thread -> DOF permutation grouping DOFs of similar
                                     //     activity into the same warps (NULL = identity)
+    const unsigned *perm_on;        // O3: device flag, 0 = ignore perm (all DOFs equally active)
 } KemLaunch;
 
 typedef struct KemModelDesc {

@@ -149,17 +149,20 @@ __global__ void k_activity_hist(const double *__restrict__ hsug, double dt, long
 __global__ void k_activity_scan(const unsigned *__restrict__ counts, unsigned *__restrict__ cursor)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned run = 0;
+        unsigned run = 0, used = 0;
         for (int k = ACT_BUCKETS - 1; k >= 0; --k) {
             cursor[k] = run;
             run += counts[k];
+            used += counts[k] != 0;
         }
+        cursor[ACT_BUCKETS] = used > 1;     // all DOFs equally active: keep the identity order
     }
 }
 
 __global__ void k_activity_scatter(const double *__restrict__ hsug, double dt, long long n,
                                    unsigned *__restrict__ cursor, int *__restrict__ perm)
 {
+    if (!cursor[ACT_BUCKETS]) return;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
@@ -494,7 +497,7 @@ int prepare_step(kem_handle h, double t0, double dt, int n_sub, int scheme, int 
             CK(cudaMemsetAsync(s.d_stats, 0, 2 * sizeof(unsigned long long), s.stream));
             CK(cudaHostAlloc((void **)&s.h_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
             CK(cudaMalloc(&s.d_perm, std::max<size_t>((size_t)s.n, 1) * sizeof(int)));
-            CK(cudaMalloc(&s.d_act, 2 * ACT_BUCKETS * sizeof(unsigned)));
+            CK(cudaMalloc(&s.d_act, (2 * ACT_BUCKETS + 1) * sizeof(unsigned)));
         }
     pl.masked = !h->shards.empty() && h->shards[0].has_mask;
     for (int s = 0; s < n_stim; ++s) {
@@ -544,7 +547,7 @@ int build_activity_perm(kem_handle h, Shard &s, double dt)
         return KEM_OK;
     }
     CK(cudaSetDevice(s.dev));
-    CK(cudaMemsetAsync(s.d_act, 0, 2 * ACT_BUCKETS * sizeof(unsigned), s.stream));
+    CK(cudaMemsetAsync(s.d_act, 0, (2 * ACT_BUCKETS + 1) * sizeof(unsigned), s.stream));
     k_activity_hist<<<grid_for(s.n), 256, 0, s.stream>>>(s.d_hsug, dt, s.n, s.d_act);
     k_activity_scan<<<1, 32, 0, s.stream>>>(s.d_act, s.d_act + ACT_BUCKETS);
     k_activity_scatter<<<grid_for(s.n), 256, 0, s.stream>>>(s.d_hsug, dt, s.n, s.d_act + ACT_BUCKETS,
@@ -602,10 +605,14 @@ int launch_range(kem_handle h, Shard &s, const StepPlan &pl, int64_t off, int64_
     L.hsug = s.d_hsug ? s.d_hsug + off : nullptr;
     L.stats = s.d_stats;
     L.perm = nullptr;
+    L.perm_on = nullptr;
     if (pl.scheme == KEM_SCHEME_DP45 && h->activity_sort && off == 0 && len == s.n) {
         int rc = build_activity_perm(h, s, pl.dt);     // whole-range launches only (not the chunks
         if (rc) return rc;                             // of kem_step_io)
-        if (s.perm_valid) L.perm = s.d_perm;
+        if (s.perm_valid) {
+            L.perm = s.d_perm;
+            L.perm_on = s.d_act + 2 * ACT_BUCKETS;
+        }
     }
     CK(cudaSetDevice(s.dev));
     cudaError_t e = m->launch(&L, s.stream);
