@@ -168,7 +168,8 @@ KEM_HD double rsqrt_seed(double x)
 
 // sqrt(x), x > 0 normal: coupled Newton step on (g ~ sqrt x, h ~ 1/(2 sqrt x)) from the
 // seed (2^-20 -> 2^-40), then one residual correction g += (x - g^2) h (-> rounding level).
-// 7 FP64 instructions + 1 MUFU.  sqrt(0) is NaN here (0 * inf); negative x gives NaN.
+// 7 FP64 instructions + 1 MUFU; sqrt(+-0) = +-0 is patched by an integer select (the
+// straight-line path would give 0 * inf); negative x gives NaN, +inf gives NaN.
 KEM_HD double sqrt(double x)
 {
     const double y = rsqrt_seed(x);
@@ -178,7 +179,8 @@ KEM_HD double sqrt(double x)
     g = fma(g, r, g);
     h = fma(h, r, h);
     const double d = fma(-g, g, x);
-    return fma(d, h, g);
+    const double res = fma(d, h, g);
+    return ((double_to_bits(x) << 1) == 0) ? x : res;
 }
 
 // x^1.5 = x sqrt(x): two roundings, <= 1 ulp (CUDA's pow is specified to 2 ulp).
@@ -206,7 +208,7 @@ static const double KEM_LOG_C_HOST[9] = KEM_LOG_TABLE;
 // log(1+f) = f - hfsq + s (hfsq + R(s^2)), hfsq = f^2/2 (the classic fdlibm arrangement;
 // coefficients from tools/fit_log_poly.py).  Straight-line; x <= 0, inf, NaN are patched
 // at the end with selects: log(0) = -inf, log(x<0) = NaN, log(inf) = inf.
-// Denormal x is treated as 0 (-inf).
+// Denormal x is treated as 0 (-inf); log(-0) = -inf.
 KEM_HD double log(double x)
 {
     const uint64_t bx = double_to_bits(x);
@@ -235,7 +237,8 @@ KEM_HD double log(double x)
     // special operands, decided on the high word in the integer pipe:
     // x < 2^-1022 (zero, denormal, any negative) and exponent field all ones (inf, NaN)
     const int hx0 = (int)(uint32_t)(bx >> 32);
-    const double low = bits_to_double(hx0 < 0 ? 0x7FF8000000000000ull : 0xFFF0000000000000ull);
+    const bool neg = hx0 < 0 && (bx << 1) != 0;        // log(-0) = -inf like log(+0)
+    const double low = bits_to_double(neg ? 0x7FF8000000000000ull : 0xFFF0000000000000ull);
     res = (hx0 < 0x00100000) ? low : res;              // -> NaN for negatives, -inf for 0
     res = (hx0 >= 0x7ff00000) ? x : res;               // +inf -> +inf, NaN -> NaN
     return res;

@@ -88,5 +88,7 @@ def test_log_special_values(hostlib):
     assert hostlib.kem_host_log(math.inf) == math.inf
     assert hostlib.kem_host_log(2.2250738585072014e-308) == math.log(2.2250738585072014e-308)
     assert hostlib.kem_host_log(1.7976931348623157e308) == math.log(1.7976931348623157e308)
+    assert hostlib.kem_host_log(-0.0) == -math.inf
     assert math.isnan(hostlib.kem_host_sqrt(-1.0))
     assert hostlib.kem_host_sqrt(4.0) == 2.0
+    assert hostlib.kem_host_sqrt(0.0) == 0.0 and math.copysign(1.0, hostlib.kem_host_sqrt(-0.0)) == -1.0
