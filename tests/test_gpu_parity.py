@@ -123,3 +123,39 @@ def test_fixed_point_known_answer(built):
     assert np.max(np.abs(S - y0) / np.abs(y0)) < 1e-9
     assert np.max(np.abs(cur[:, 0] + cur[:, 1])) < 1e-9       # I_ch_Na + I_ch_K ~ 0
     assert np.all(cur[:, 2] == 0.0)                            # I_ch_Cl is the constant 0.0
+
+
+def test_removable_singularity_of_the_rate_functions(built):
+    """alpha_m = 0.1 (V+40) / (1 - exp(-(V+40)/10)) (tissue mm_hh.py:163) is 0/0 at V = -40 mV
+    and amplifies the last-bit error of exp by 10/|V+40| next to it.  The kernel keeps the
+    reference's form (exp(x) - 1, not expm1), so it errs like the reference does: parity holds
+    down to |V+40| = 1e-4 mV, and the exact singular point fails on both sides
+    (`assert success`, odeSolver.py:121)."""
+    from knpemi_b200.ducks import PointSpace
+    from knpemi_b200.odeSolver import MembraneModel
+    from oracle import cpu_oracle
+    name = "hh_tissue"
+    ode = builtin(name)
+    offsets = np.array([1e-2, -1e-2, 1e-3, -1e-3, 1e-4, -1e-4])
+    n = len(offsets)
+    S = np.tile(ode.init_state_values(), (n, 1))
+    S[:, 3] = -40.0 + offsets
+    p = ode.init_parameter_values()
+    for k, v in {**SETUP[name]["uniform"], **SETUP[name]["varying"]}.items():
+        p[ode.parameter_indices(k)] = v
+    P = np.tile(p, (n, 1))
+    m = MembraneModel(ode, None, 1, PointSpace(np.zeros((n, 3))), devices=[0], verbose=False, n_sub=1)
+    load_tables(m, S, P)
+    m.step_lsoda(1e-3, None)                    # one RK4 step of 1 us: the states stay next to -40 mV
+    assert cpu_oracle.step(name, S, P, 0.0, 1e-3, 1) == 0
+    assert rel_err(np.asarray(m.states), S, scales(S)) < RTOL
+    m.close()
+    # exactly on the singularity: 0/0 -> NaN on both sides
+    S1 = np.tile(ode.init_state_values(), (1, 1))
+    S1[0, 3] = -40.0
+    m = MembraneModel(ode, None, 1, PointSpace(np.zeros((1, 3))), devices=[0], verbose=False)
+    load_tables(m, S1, P[:1])
+    with pytest.raises(AssertionError):
+        m.step_lsoda(0.1, None)
+    assert cpu_oracle.step(name, S1, P[:1].copy(), 0.0, 0.1, 25) == 1
+    m.close()
