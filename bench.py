@@ -193,7 +193,8 @@ def fp64_slots(model_name: str, n_sub: int):
         return None, None
     if e.get("ncu_per_dof_step") and e.get("ncu_n_sub") == n_sub:
         return float(e["ncu_per_dof_step"]), "ncu"
-    return float(4 * n_sub * e["loop_fp64"] + e["once_fp64"]), "sass-static"
+    iters = 4 // int(e.get("stages_per_loop_iteration", 1))
+    return float(iters * n_sub * e["loop_fp64"] + e["once_fp64"]), "sass-static"
 
 
 def host_threads() -> int:

@@ -112,9 +112,8 @@ kem_step_kernel(const __grid_constant__ KemArgs<M> a)
 
     // ---- classical RK4, association identical to oracle/knpemi_oracle.c:step_row:
     //        acc = ((k1 + 2 k2) + 2 k3) + k4 ;  y += (h/6) acc
-    // The four stages run through ONE copy of the right-hand side (stage loop not
-    // unrolled): a quarter of the code, so the sub-step loop stays in the
-    // instruction cache.
+    // (With CUDA's libm the four inlined stages were a 59 KB loop body that missed the
+    // instruction cache; with the branch-free math of kem_math.cuh one sub-step is ~13 KB.)
     double w[NS];
 #pragma unroll
     for (int c = 0; c < NS; ++c) w[c] = y[c];
@@ -124,7 +123,10 @@ kem_step_kernel(const __grid_constant__ KemArgs<M> a)
         double acc[NS];
 #pragma unroll
         for (int c = 0; c < NS; ++c) acc[c] = 0.0;
-#pragma unroll 1
+        // M::STAGE_UNROLL = 4 (the default for all but very large right-hand sides) takes the
+        // four stages inline: stage weights become immediates and the loop control disappears
+        // from the instruction stream (hh_ideal: 42 -> 32 non-FP64 instructions per stage)
+#pragma unroll(M::STAGE_UNROLL)
         for (int s = 0; s < 4; ++s) {
             double k[NS];
             M::deriv(w, k, q, tj + ((s + 1) >> 1) * NT);      // stage times ta, tb, tb, tc

@@ -71,9 +71,13 @@ def table(out_path):
             if "kem_step_kernel" in kname and "ELi128E" in kname:
                 c, dp, n = summarize(insts)
                 lc, ldp, ln = summarize(inner_loop(insts))
+                m_unroll = re.search(r"STAGE_UNROLL = (\d+);", em.source)
+                stages_per_loop = int(m_unroll.group(1)) if m_unroll else 1
+                iters = 4 // stages_per_loop                  # loop iterations per RK4 sub-step
                 e = {"source_hash": em.source_hash, "instructions": n, "fp64": dp,
                      "loop_instructions": ln, "loop_fp64": ldp, "once_fp64": dp - ldp,
-                     "static_per_dof_step_n_sub_25": 100 * ldp + (dp - ldp)}
+                     "stages_per_loop_iteration": stages_per_loop,
+                     "static_per_dof_step_n_sub_25": 25 * iters * ldp + (dp - ldp)}
                 prev = old.get(name, {})
                 if prev.get("source_hash") == em.source_hash:       # keep ncu-measured figures
                     for k in ("ncu_per_dof_step", "ncu_n_sub", "ncu_dram_bytes_per_dof_step", "ncu_report"):
