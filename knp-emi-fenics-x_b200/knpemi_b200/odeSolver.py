@@ -38,6 +38,7 @@ from .codegen import EmitOptions, model_library
 __all__ = ["MembraneModel", "TableView", "KemError", "NonFiniteStateError"]
 
 _SAMPLE_ROWS = 24
+_MASK_CACHE_ENTRIES = 8
 
 
 def _default_devices():
@@ -448,6 +449,8 @@ class MembraneModel:
         mask = self._rows_of(locator)
         if mask.all():
             mask = None        # every row selected: same as no locator
+        if len(self._mask_cache) >= _MASK_CACHE_ENTRIES:     # a caller that builds a new lambda
+            self._mask_cache.pop(next(iter(self._mask_cache)))   # per step must not pile up masks
         self._mask_cache[id(locator)] = (locator, mask)
         return mask
 
