@@ -410,6 +410,8 @@ class MembraneModel:
 
     def _host_array(self, u, writable):
         a = u.x.array if hasattr(u, "x") else u
+        if not isinstance(a, np.ndarray) and hasattr(a, "__dlpack__"):
+            a = np.from_dlpack(a)                   # zero-copy view of a CPU DLPack tensor
         if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous
                 and a.ndim == 1 and len(a) >= self.nodes and (a.flags.writeable or not writable)):
             raise KemError("step_exchange needs 1-D contiguous float64 host arrays of length >= N")

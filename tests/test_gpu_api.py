@@ -391,3 +391,24 @@ def test_large_sub_step_counts_and_their_limit(built):
     with pytest.raises(KemError):
         m.step(0.1, None, n_sub=0)
     m.close()
+
+
+def test_step_exchange_accepts_dlpack_host_tensors(built):
+    """north_star: 'a thin ctypes/C-ABI layer that passes DLPack/NumPy pointers' -- a CPU DLPack
+    producer (here a torch tensor) is viewed without a copy."""
+    torch = pytest.importorskip("torch")
+    from knpemi_b200.odeSolver import MembraneModel
+    n = 5000
+    S, P, X, mask = synthetic_tables("hh_test", n, seed=2)
+    a = MembraneModel(builtin("hh_test"), None, 1, Space(X), verbose=False, devices=[0])
+    b = MembraneModel(builtin("hh_test"), None, 1, Space(X), verbose=False, devices=[0])
+    for m in (a, b):
+        load_tables(m, S, P)
+    v_in = torch.from_numpy(S[:, 3].copy() * 1.01)
+    v_out = torch.zeros(n, dtype=torch.float64)
+    a.step_exchange(0.1, {("state", "V"): v_in}, {("state", "V"): v_out})
+    b.set_membrane_potential(Func(v_in.numpy()))
+    b.step_lsoda(0.1, None)
+    assert np.array_equal(v_out.numpy(), b.states[:, 3])
+    a.close()
+    b.close()
