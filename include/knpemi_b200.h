@@ -165,6 +165,10 @@ int kem_device_scatter(kem_handle h, int shard, int kind, int col, double *dev_d
 /* table[i, col] = dev_a[map_a[i]] - dev_b[map_b[i]]   (phi_M = tr(phi_i) - tr(phi_e), utils.py:247-293) */
 int kem_device_gather_diff(kem_handle h, int shard, int kind, int col, const double *dev_a,
                            int map_a, const double *dev_b, int map_b);
+/* contiguous device-to-device column copies for the DOFs of shard k (no map):
+ * table[begin_k:end_k, col] = dev_src[0:n_k]   and   dev_dst[0:n_k] = table[begin_k:end_k, col] */
+int kem_device_copy_in(kem_handle h, int shard, int kind, int col, const double *dev_src);
+int kem_device_copy_out(kem_handle h, int shard, int kind, int col, double *dev_dst);
 /* plain device buffers for callers without their own CUDA allocations (tests, Python hosts) */
 int kem_device_alloc(int dev, size_t bytes, void **ptr_out);
 int kem_device_free(int dev, void *ptr);

@@ -1430,6 +1430,43 @@ int kem_device_gather_diff(kem_handle h, int shard, int kind, int col, const dou
     return KEM_OK;
 }
 
+int kem_device_copy_in(kem_handle h, int shard, int kind, int col, const double *dev_src)
+{
+    int rc = check_col(h, kind, col, __func__);
+    if (rc) return rc;
+    ARG(shard >= 0 && shard < (int)h->shards.size(), "shard out of range");
+    if (kind == KEM_PARAM && (h->p_uniform[col] || !h->shards[0].pcol[col])) {
+        rc = ensure_pcol(h, col);
+        if (rc) return rc;
+    }
+    Shard &s = h->shards[shard];
+    if (s.n == 0) return KEM_OK;
+    ARG(dev_src, "null device pointer");
+    CK(cudaSetDevice(s.dev));
+    CK(cudaMemcpyAsync(col_ptr(s, kind, col), dev_src, (size_t)s.n * sizeof(double), cudaMemcpyDeviceToDevice,
+                       s.stream));
+    return KEM_OK;
+}
+
+int kem_device_copy_out(kem_handle h, int shard, int kind, int col, double *dev_dst)
+{
+    int rc = check_col(h, kind, col, __func__);
+    if (rc) return rc;
+    ARG(shard >= 0 && shard < (int)h->shards.size(), "shard out of range");
+    if (kind == KEM_PARAM && h->p_uniform[col]) {
+        rc = ensure_pcol(h, col);
+        if (rc) return rc;
+    }
+    Shard &s = h->shards[shard];
+    if (s.n == 0) return KEM_OK;
+    ARG(dev_dst, "null device pointer");
+    CK(cudaSetDevice(s.dev));
+    CK(cudaMemcpyAsync(dev_dst, col_ptr(s, kind, col), (size_t)s.n * sizeof(double), cudaMemcpyDeviceToDevice,
+                       s.stream));
+    CK(cudaStreamSynchronize(s.stream));     // the caller's own stream may read dev_dst next
+    return KEM_OK;
+}
+
 int kem_device_alloc(int dev, size_t bytes, void **ptr_out)
 {
     ARG(ptr_out, "null output");

@@ -90,6 +90,8 @@ SIGNATURES = {
     "kem_device_scatter": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "kem_device_gather_diff": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                          C.c_int]),
+    "kem_device_copy_in": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "kem_device_copy_out": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "kem_device_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
     "kem_device_free": (C.c_int, [C.c_int, C.c_void_p]),
     "kem_device_upload": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -369,6 +369,46 @@ class MembraneModel:
                                                C.c_void_p(phi_e_ptr), int(map_e)), "kem_device_gather_diff")
         return self.states
 
+    @staticmethod
+    def _cuda_pointer(arr, n, writable):
+        '''Device pointer of a CUDA array (torch.cuda / CuPy / Numba: __cuda_array_interface__).'''
+        cai = getattr(arr, "__cuda_array_interface__", None)
+        if cai is None:
+            raise KemError("expected an object with __cuda_array_interface__ (a CUDA array)")
+        if cai["typestr"] not in ("<f8", "=f8") or cai.get("strides") not in (None, (8,)) \
+                or len(cai["shape"]) != 1 or cai["shape"][0] < n:
+            raise KemError("CUDA array must be 1-D contiguous float64 with at least N entries")
+        ptr, readonly = cai["data"]
+        if writable and readonly:
+            raise KemError("CUDA array is read-only")
+        return ptr
+
+    def set_from_cuda_array(self, what, which, arr, shard=0):
+        '''table[range of shard, which] = arr[:n_shard] for a CUDA array on that shard's device
+        (device-to-device; no host round trip, no map).'''
+        kind, col = self._kind_col(what, which)
+        n = self.shard_ranges()[shard][2] - self.shard_ranges()[shard][1]
+        check(self._lib.kem_device_copy_in(self._h, shard, kind, col,
+                                           C.c_void_p(self._cuda_pointer(arr, n, False))), "kem_device_copy_in")
+        return self.states
+
+    def get_to_cuda_array(self, what, which, arr, shard=0):
+        '''arr[:n_shard] = table[range of shard, which] for a CUDA array on that shard's device.'''
+        kind, col = self._kind_col(what, which)
+        n = self.shard_ranges()[shard][2] - self.shard_ranges()[shard][1]
+        check(self._lib.kem_device_copy_out(self._h, shard, kind, col,
+                                            C.c_void_p(self._cuda_pointer(arr, n, True))), "kem_device_copy_out")
+        return arr
+
+    def shard_ranges(self):
+        '''[(device, begin, end)] of the contiguous DOF ranges of this model's devices.'''
+        out = []
+        for k in range(len(self.devices)):
+            dev, b, e = C.c_int(), C.c_int64(), C.c_int64()
+            check(self._lib.kem_shard_range(self._h, k, C.byref(dev), C.byref(b), C.byref(e)), "kem_shard_range")
+            out.append((dev.value, b.value, e.value))
+        return out
+
     # ------------------------------------------------------------------ helpers
     def timer_begin(self):
         '''Record a CUDA event on every device's launching stream.'''

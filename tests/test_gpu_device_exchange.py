@@ -53,3 +53,32 @@ def test_gather_scatter_and_potential_jump(built):
         d.free()
     a.close()
     b.close()
+
+
+def test_cuda_array_interface_columns(built):
+    """Device-to-device column copies from / to CUDA arrays of another library (torch here)."""
+    torch = pytest.importorskip("torch")
+    from knpemi_b200._cabi import KemError
+    from knpemi_b200.odeSolver import MembraneModel
+    name, n = "hh_ideal", 20_001
+    S, P, X, mask = synthetic_tables(name, n, seed=4)
+    ode = builtin(name)
+    a = MembraneModel(ode, None, 1, Space(X), verbose=False, devices=[0])
+    b = MembraneModel(ode, None, 1, Space(X), verbose=False, devices=[0])
+    for m in (a, b):
+        load_tables(m, S, P)
+    assert a.shard_ranges() == [(0, 0, n)]
+    k_e = torch.tensor(3.3 * (1 + 0.01 * np.random.default_rng(0).uniform(-1, 1, n)), device="cuda:0")
+    a.set_from_cuda_array('parameter', 'K_e', k_e)
+    b.set_parameter('K_e', Func(k_e.cpu().numpy()))
+    for m in (a, b):
+        m.step_lsoda(1e-4, {'stim_amplitude': 10.0}, lambda x: x[0] < 20e-6)
+    out = torch.zeros(n, dtype=torch.float64, device="cuda:0")
+    a.get_to_cuda_array('state', 'V', out)
+    assert np.array_equal(out.cpu().numpy(), b.states[:, 3])
+    with pytest.raises(KemError):
+        a.set_from_cuda_array('parameter', 'K_e', torch.zeros(n, dtype=torch.float32, device="cuda:0"))
+    with pytest.raises(KemError):
+        a.set_from_cuda_array('parameter', 'K_e', np.zeros(n))
+    a.close()
+    b.close()
