@@ -155,7 +155,10 @@ int kem_timer_end(kem_handle h, double *ms_out);
  * copies and four getter copies of one PDE step (utils.py:217-233, run_2D.py:105-109)
  * become index gathers / scatters over membrane-DOF -> bulk-DOF maps (a CG-1 trace is a
  * vertex copy: utils.py:150-207), with no host traffic.  Maps are registered once;
- * `shard` selects the handle's k-th device, and the device pointers must live there. */
+ * `shard` selects the handle's k-th device, and the device pointers must live there.
+ * Ordering: these calls enqueue on the handle's own stream; the caller makes sure its
+ * producer of `dev_src` has finished (synchronise that stream or event) before calling, and
+ * kem_device_scatter / kem_device_copy_out return after the data has landed. */
 /* register map `map_id` (0..15): bulk index of every membrane DOF, n = n_dof entries */
 int kem_device_map_set(kem_handle h, int map_id, const int64_t *host_map, int64_t n);
 /* table[i, col] = dev_src[map[i]]             (update_ode_variables, utils.py:224-228) */

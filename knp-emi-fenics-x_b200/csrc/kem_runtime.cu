@@ -1406,6 +1406,7 @@ int kem_device_scatter(kem_handle h, int shard, int kind, int col, double *dev_d
     k_scatter<<<grid_for(s.n), 256, 0, s.stream>>>(dev_dst, col_ptr(s, kind, col), s.d_map[map_id], s.n);
     CK(cudaGetLastError());
     h->launches++;
+    CK(cudaStreamSynchronize(s.stream));     // the caller's own stream may read dev_dst next
     return KEM_OK;
 }
 
