@@ -94,3 +94,18 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "libknpemi_oracle" not in text, f
                 assert "kemo_" not in text, f
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The boundary is a C ABI: the header must compile as C (no C++-isms, no CUDA types)."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "knpemi_b200.h"\nint main(void) { kem_handle h = 0; (void)h; return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I",
+                        os.path.join(ROOT, "include"), "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(HEADER).read()
+    assert "cuda" not in text.lower().replace("cuda device", "").replace("cuda errors", "").replace(
+        "cuda arrays", "").replace("cuda-event", "").replace("cuda events", "").replace("cuda allocations", "") \
+        or "cudaStream_t" not in text
+    assert "torch" not in text.lower()
