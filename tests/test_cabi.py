@@ -105,7 +105,5 @@ def test_header_is_plain_c99(tmp_path):
                         os.path.join(ROOT, "include"), "-fsyntax-only", str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     text = open(HEADER).read()
-    assert "cuda" not in text.lower().replace("cuda device", "").replace("cuda errors", "").replace(
-        "cuda arrays", "").replace("cuda-event", "").replace("cuda events", "").replace("cuda allocations", "") \
-        or "cudaStream_t" not in text
+    assert "cudaStream_t" not in text and "#include <cuda" not in text
     assert "torch" not in text.lower()
