@@ -125,7 +125,7 @@ kem_step_kernel(const __grid_constant__ KemArgs<M> a)
         for (int c = 0; c < NS; ++c) acc[c] = 0.0;
         // M::STAGE_UNROLL = 4 (the default for all but very large right-hand sides) takes the
         // four stages inline: stage weights become immediates and the loop control disappears
-        // from the instruction stream (hh_ideal: 42 -> 32 non-FP64 instructions per stage)
+        // from the instruction stream (hh_ideal: 42 -> 24.5 non-FP64 instructions per stage)
 #pragma unroll(M::STAGE_UNROLL)
         for (int s = 0; s < 4; ++s) {
             double k[NS];
