@@ -126,12 +126,13 @@ class ClockSampler:
 class Dist:
     """torch.distributed plumbing for N > 1 (barrier + max over ranks); no-op for N = 1."""
 
-    def __init__(self):
+    def __init__(self, init=True):
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         self.torch = None
-        if self.world > 1:
+        self.backend = None
+        if self.world > 1 and init:
             import torch
             import torch.distributed as dist
             self.torch, self.dist = torch, dist
@@ -174,7 +175,7 @@ class Dist:
         return [float(v) for v in t.tolist()]
 
     def close(self):
-        if self.world > 1:
+        if self.world > 1 and self.torch is not None:
             self.dist.destroy_process_group()
 
 
@@ -546,7 +547,8 @@ def main():
     os.dup2(2, 1)
     global _emit
     _emit = lambda line: (real_stdout.write(line + "\n"), real_stdout.flush())     # noqa: E731
-    dist = Dist()
+    # the reference arm is CPU work on rank 0 only: no process group, the other ranks just exit
+    dist = Dist(init=args.impl != "reference")
     if dist.world != args.gpus and dist.world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={dist.world}")
     if args.gpus > 1 and dist.world == 1:
