@@ -24,7 +24,7 @@ from dataclasses import dataclass
 from .ir import P, S, T, Dag, ModelSourceError
 from .parse import ParsedModel
 
-CODEGEN_VERSION = "8"
+CODEGEN_VERSION = "9"
 
 
 @dataclass
@@ -185,9 +185,15 @@ class _Emitter:
             return f"pow({a[0]}, {a[1]})"
         if op == "mod":
             return f"kem_npmod({a[0]}, {a[1]})" if ctx != "time" else f"kem_npmod_host({a[0]}, {a[1]})"
-        if op in ("lt", "le", "gt", "ge"):
-            sym = {"lt": "<", "le": "<=", "gt": ">", "ge": ">="}[op]
+        if op in ("lt", "le", "gt", "ge", "eq", "ne"):
+            sym = {"lt": "<", "le": "<=", "gt": ">", "ge": ">=", "eq": "==", "ne": "!="}[op]
             return f"(double)({a[0]} {sym} {a[1]})"
+        if op == "call1":
+            return f"{n.val}({a[0]})"
+        if op == "call2":
+            return f"{n.val}({a[0]}, {a[1]})"
+        if op == "select":
+            return f"(({a[0]}) != 0.0 ? ({a[1]}) : ({a[2]}))"
         raise AssertionError(op)
 
     def powi_lines(self, nid: int, ctx: str, indent: str) -> list:

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import math
 
-from .ir import int_pow, np_mod
+from .ir import CALL1, CALL2, int_pow, np_mod
 from .parse import ParsedModel
 
 
@@ -52,8 +52,15 @@ def evaluate(pm: ParsedModel, t: float, y, p):
             v = int_pow(a[0], int(n.val))
         elif op == "mod":
             v = np_mod(a[0], a[1])
-        elif op in ("lt", "le", "gt", "ge"):
-            v = float({"lt": a[0] < a[1], "le": a[0] <= a[1], "gt": a[0] > a[1], "ge": a[0] >= a[1]}[op])
+        elif op in ("lt", "le", "gt", "ge", "eq", "ne"):
+            v = float({"lt": a[0] < a[1], "le": a[0] <= a[1], "gt": a[0] > a[1], "ge": a[0] >= a[1],
+                       "eq": a[0] == a[1], "ne": a[0] != a[1]}[op])
+        elif op == "call1":
+            v = float(CALL1[n.val](a[0]))
+        elif op == "call2":
+            v = float(CALL2[n.val](a[0], a[1]))
+        elif op == "select":
+            v = a[1] if a[0] != 0.0 else a[2]
         else:
             raise AssertionError(op)
         val[nid] = v

@@ -25,8 +25,17 @@ from dataclasses import dataclass, field
 
 P, S, T = "P", "S", "T"
 
-BINOPS = ("add", "sub", "mul", "div", "pow", "mod", "lt", "le", "gt", "ge")
+BINOPS = ("add", "sub", "mul", "div", "pow", "mod", "lt", "le", "gt", "ge", "eq", "ne")
 UNOPS = ("neg", "exp", "log", "sqrt")
+
+#: further libm functions a model may call (beyond what the reference's models use); they go
+#: to CUDA's libm on the device and to Python's math module when constants are folded
+CALL1 = {"fabs": math.fabs, "tanh": math.tanh, "sinh": math.sinh, "cosh": math.cosh,
+         "sin": math.sin, "cos": math.cos, "tan": math.tan, "atan": math.atan,
+         "asin": math.asin, "acos": math.acos, "floor": math.floor, "ceil": math.ceil,
+         "log10": math.log10, "log1p": math.log1p, "expm1": math.expm1, "erf": math.erf}
+CALL2 = {"fmin": min, "fmax": max, "atan2": math.atan2, "copysign": math.copysign,
+         "fmod": math.fmod}
 
 
 class ModelSourceError(ValueError):
@@ -123,6 +132,25 @@ class Dag:
                 raise ModelSourceError(f"constant {op}({x}) is not finite: {e}")
         return self._intern(Node(op, (a,)), self.deps[a])
 
+    def call1(self, name: str, a: int) -> int:
+        if self.is_const(a):
+            try:
+                return self.const(float(CALL1[name](self.fvalue(a))))
+            except (ValueError, OverflowError) as e:
+                raise ModelSourceError(f"constant {name}({self.fvalue(a)}) failed: {e}")
+        return self._intern(Node("call1", (a,), name), self.deps[a])
+
+    def call2(self, name: str, a: int, b: int) -> int:
+        if self.is_const(a) and self.is_const(b):
+            return self.const(float(CALL2[name](self.fvalue(a), self.fvalue(b))))
+        return self._intern(Node("call2", (a, b), name), self.deps[a] | self.deps[b])
+
+    def select(self, cond: int, a: int, b: int) -> int:
+        """`a if cond else b` with cond a 0/1 (or any zero / non-zero) value."""
+        if self.is_const(cond):
+            return a if self.fvalue(cond) != 0.0 else b
+        return self._intern(Node("select", (cond, a, b)), self.deps[cond] | self.deps[a] | self.deps[b])
+
     def binary(self, op: str, a: int, b: int) -> int:
         if self.is_const(a) and self.is_const(b):
             return self._fold_binary(op, a, b)
@@ -157,8 +185,8 @@ class Dag:
             elif op == "mod":
                 r = np_mod(float(x), float(y))
                 both_int = False
-            elif op in ("lt", "le", "gt", "ge"):
-                r = {"lt": x < y, "le": x <= y, "gt": x > y, "ge": x >= y}[op]
+            elif op in ("lt", "le", "gt", "ge", "eq", "ne"):
+                r = {"lt": x < y, "le": x <= y, "gt": x > y, "ge": x >= y, "eq": x == y, "ne": x != y}[op]
                 return self.iconst(int(r))
             else:
                 raise ModelSourceError(f"cannot fold {op}")

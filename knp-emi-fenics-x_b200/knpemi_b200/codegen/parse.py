@@ -10,7 +10,7 @@ from __future__ import annotations
 import ast
 from dataclasses import dataclass
 
-from .ir import Dag, ModelSourceError
+from .ir import CALL1, CALL2, Dag, ModelSourceError
 
 _CALLS = {
     ("math", "exp"): "exp", ("np", "exp"): "exp", ("numpy", "exp"): "exp",
@@ -21,7 +21,10 @@ _CALLS = {
 }
 _BIN = {ast.Add: "add", ast.Sub: "sub", ast.Mult: "mul", ast.Div: "div", ast.Pow: "pow",
         ast.Mod: "mod"}
-_CMP = {ast.Lt: "lt", ast.LtE: "le", ast.Gt: "gt", ast.GtE: "ge"}
+_CMP = {ast.Lt: "lt", ast.LtE: "le", ast.Gt: "gt", ast.GtE: "ge", ast.Eq: "eq", ast.NotEq: "ne"}
+# spellings of the extra libm functions: math.*, np.*, and the builtins abs/min/max
+_ALIASES = {"abs": "fabs", "absolute": "fabs", "arctan": "atan", "arcsin": "asin", "arccos": "acos",
+            "arctan2": "atan2", "minimum": "fmin", "maximum": "fmax", "min": "fmin", "max": "fmax"}
 
 
 @dataclass
@@ -101,8 +104,19 @@ def parse_model_source(source: str, filename: str = "<model>", func_name: str = 
             return simplify_bin(op, expr(node.left), expr(node.right))
         if isinstance(node, ast.Compare):
             if len(node.ops) != 1 or type(node.ops[0]) not in _CMP:
-                raise err(node, "only single <, <=, >, >= comparisons are supported")
+                raise err(node, "only single <, <=, >, >=, ==, != comparisons are supported")
             return dag.binary(_CMP[type(node.ops[0])], expr(node.left), expr(node.comparators[0]))
+        if isinstance(node, ast.IfExp):
+            return dag.select(expr(node.test), expr(node.body), expr(node.orelse))
+        if isinstance(node, ast.BoolOp):
+            vals = [dag.binary("ne", expr(v), dag.iconst(0)) for v in node.values]
+            acc = vals[0]
+            for v in vals[1:]:
+                if isinstance(node.op, ast.And):
+                    acc = dag.binary("mul", acc, v)                       # both 0/1
+                else:
+                    acc = dag.binary("gt", dag.binary("add", acc, v), dag.iconst(0))
+            return acc
         if isinstance(node, ast.Call):
             f = node.func
             key = None
@@ -111,6 +125,15 @@ def parse_model_source(source: str, filename: str = "<model>", func_name: str = 
             elif isinstance(f, ast.Name):
                 key = ("math", f.id)
             op = _CALLS.get(key)
+            if op is None and key is not None and key[0] in ("math", "np", "numpy") and not node.keywords:
+                name = _ALIASES.get(key[1], key[1])
+                args = [expr(a) for a in node.args]
+                if name in CALL1 and len(args) == 1:
+                    return dag.call1(name, args[0])
+                if name in CALL2 and len(args) == 2:
+                    return dag.call2(name, args[0], args[1])
+                if name == "where" and len(args) == 3:
+                    return dag.select(args[0], args[1], args[2])
             if op is None or node.keywords:
                 raise err(node, f"unsupported call {ast.unparse(f)}")
             args = [expr(a) for a in node.args]

@@ -109,10 +109,13 @@ def test_docstrings_and_comment_blocks_are_skipped():
 
 @pytest.mark.parametrize("body,msg", [
     (["for i in range(3):", "    values[0] = 1.0"], "only simple assignments"),
-    (["values[0] = math.sin(states[0])"], "unsupported call"),
+    (["values[0] = math.gamma(states[0])"], "unsupported call"),
+    (["values[0] = helper(states[0])"], "unsupported call"),
     (["values[0] = states[i]"], "integer literals"),
     (["values[0] = undefined_name"], "not defined"),
-    (["values[0] = states[0] if t > 0 else 1.0"], "unsupported expression"),
+    (["values[0] = [states[0]][0]"], "unsupported subscript"),
+    (["values[0] = (lambda x: x)(states[0])"], "unsupported call"),
+    (["values[0] = 0 < states[0] < 1"], "only single"),
     (["parameters[0] = 1.0", "values[0] = parameters[0]"], "read after"),
     (["x = 1.0"], "assigns no values"),
     (["values[1] = 1.0"], "outside the 1 states"),
@@ -150,3 +153,32 @@ def test_committed_sample_of_generated_code_is_current(name):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     with open(os.path.join(root, "docs", f"generated_{name}.cu")) as f:
         assert f.read() == codegen.generate(builtin(name)).source
+
+
+def test_conditionals_and_extra_libm_calls():
+    """Beyond what the reference's six models use, but common in Gotran-generated modules:
+    `a if c else b`, and/or, ==/!=, np.where, abs/tanh/min/max/... (CUDA libm on the device)."""
+    import math
+    body = [
+        "v = states[0]",
+        "gate = 1.0 if v > 0.5 else 0.25",
+        "both = (v > 0.1 and parameters[0] != 0) or v == 7",
+        "w = np.where(v < 0, -v, v) + abs(v - 1) + math.tanh(v) + min(v, 0.3) + np.maximum(v, 0.6)",
+        "values[0] = gate * w + both + math.floor(2.5) + np.log1p(v * v) + math.atan2(v, 2.0)",
+        "parameters[1] = math.fmod(v, 0.3) + math.cos(0.0)",
+    ]
+    src = _src(body)
+    pm = parse_model_source(src)
+    for v, p0 in ((0.7, 1.0), (0.2, 0.0), (-0.4, 2.0), (7.0, 0.0)):
+        dy, p_after = evaluate(pm, 0.0, [v], [p0, 0.0])
+        gate = 1.0 if v > 0.5 else 0.25
+        both = float((v > 0.1 and p0 != 0) or v == 7)
+        w = (-v if v < 0 else v) + abs(v - 1) + math.tanh(v) + min(v, 0.3) + max(v, 0.6)
+        want = gate * w + both + 2.0 + math.log1p(v * v) + math.atan2(v, 2.0)
+        assert dy[0] == pytest.approx(want, rel=1e-15)
+        assert p_after[1] == pytest.approx(math.fmod(v, 0.3) + 1.0, rel=1e-15)
+    em = generate_from_source(src, "cond", 1, 2)
+    dev = em.source.split("static void tonly")[0]
+    for token in ("tanh(", "fabs(", "fmin(", "fmax(", "log1p(", "atan2(", "fmod(", "!= 0.0 ?"):
+        assert token in dev, token
+    assert "floor(" not in dev                     # folded constant

@@ -39,8 +39,14 @@ def random_expr(rng, depth, leaves):
         return f"np.sqrt(1.0 + ({a})**2)"
     if kind < 0.94:
         return f"math.log(2.0 + ({a})**2)"
-    if kind < 0.97:
+    if kind < 0.955:
         return f"(0.5 + ({a})**2) ** 1.5"
+    if kind < 0.965:
+        return f"(({a}) if ({b}) > 0.05 else ({b}) * 0.5)"                  # conditional expression
+    if kind < 0.975:
+        return f"math.tanh({a})"
+    if kind < 0.985:
+        return f"(abs({a}) + min({a}, {b}) - np.maximum({b}, 0.1))"
     return f"math.pow({a}, {rng.choice([2, 3, 4])})"
 
 
@@ -91,7 +97,7 @@ def numpy_rk4(pm, S, P, t0, dt, n_sub):
     return S, P
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(10))
 @pytest.mark.parametrize("mode", ["fast", "libm"])
 def test_random_model_matches_interpreter(built, tmp_path, seed, mode):
     from knpemi_b200.codegen import EmitOptions, parse_model_source
