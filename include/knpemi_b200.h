@@ -46,7 +46,7 @@ typedef struct kem_model_info {
     int n_out;       /* parameter slots the RHS writes (I_ch_*; mm_hh.py:220-225) */
     int n_used;      /* parameter slots the RHS reads */
     int n_tslots;    /* host-evaluated time-only factors per stage time */
-    int out_cols[16];
+    int out_cols[64];
     char name[64];
     char source_hash[32];
 } kem_model_info;

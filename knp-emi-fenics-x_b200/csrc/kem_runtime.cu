@@ -691,7 +691,7 @@ int kem_model_load(const char *so_path, int *model_id_out)
         dlclose(dl);
         return fail(KEM_E_MODEL, std::string(so_path) + ": model ABI version mismatch (regenerate)");
     }
-    if (d->ns < 1 || d->np < 0 || d->n_out < 0 || d->n_out > 16 || !d->launch || !d->tonly) {
+    if (d->ns < 1 || d->np < 0 || d->n_out < 0 || d->n_out > 64 || !d->launch || !d->tonly) {
         dlclose(dl);
         return fail(KEM_E_MODEL, std::string(so_path) + ": malformed model descriptor");
     }

@@ -33,7 +33,7 @@ class NonFiniteStateError(AssertionError):
 
 class kem_model_info(C.Structure):
     _fields_ = [("ns", C.c_int), ("np", C.c_int), ("n_out", C.c_int), ("n_used", C.c_int),
-                ("n_tslots", C.c_int), ("out_cols", C.c_int * 16), ("name", C.c_char * 64),
+                ("n_tslots", C.c_int), ("out_cols", C.c_int * 64), ("name", C.c_char * 64),
                 ("source_hash", C.c_char * 32)]
 
 

@@ -46,7 +46,7 @@ def test_structs_match_the_header_layout(built):
     from knpemi_b200 import _cabi
     assert ctypes.sizeof(_cabi.kem_step_times) == 4 * 8
     assert ctypes.sizeof(_cabi.kem_io_column) == 16
-    assert ctypes.sizeof(_cabi.kem_model_info) == 5 * 4 + 16 * 4 + 64 + 32
+    assert ctypes.sizeof(_cabi.kem_model_info) == 5 * 4 + 64 * 4 + 64 + 32
 
 
 def test_generated_model_libraries_export_one_descriptor(built):

@@ -86,3 +86,54 @@ def test_device_exp_div_rcp_within_one_ulp_of_libm(built, tmp_path):
     # reciprocal is faithful (<= 0.51 ulp): it may differ from IEEE in the last bit, rarely
     assert np.array_equal(fast[:, 1], libm[:, 1])
     assert np.mean(fast[:, 2] != libm[:, 2]) < 0.02
+
+
+def test_extra_libm_functions_and_conditionals_on_device(built, tmp_path):
+    """Every function of codegen.ir.CALL1 / CALL2 plus select/and/or through the real path,
+    against the DAG interpreter (Python's math module)."""
+    from knpemi_b200.codegen import parse_model_source
+    from knpemi_b200.codegen.interpret import evaluate
+    from knpemi_b200.codegen.ir import CALL1, CALL2
+    from knpemi_b200.odeSolver import MembraneModel
+    one = sorted(CALL1)
+    two = sorted(CALL2)
+    n_out = len(one) + len(two) + 3
+    lines = ["import math", "import numpy as np", "def init_state_values(**values):",
+             "    return np.array([0.3, 0.7], dtype=np.float64)", "def init_parameter_values(**values):",
+             f"    return np.zeros({n_out}, dtype=np.float64)", "def state_indices(*names):",
+             "    d = {'V': 0, 'w': 1}", "    r = [d[n] for n in names]", "    return r if len(r) > 1 else r[0]",
+             "def parameter_indices(*names):", "    return 0",
+             "def rhs_numba(t, states, values, parameters):", "    x = states[0]", "    y = states[1]"]
+    for k, f in enumerate(one):
+        arg = "x * 0.9" if f in ("asin", "acos") else ("x * x" if f == "log1p" else "x")
+        lines.append(f"    parameters[{k}] = math.{f}({arg})")
+    for k, f in enumerate(two):
+        lines.append(f"    parameters[{len(one) + k}] = math.{f}(x, y)")
+    base = len(one) + len(two)
+    lines += [f"    parameters[{base}] = x if x > y else y * 2",
+              f"    parameters[{base + 1}] = 1.0 * (x > 0 and y > 0.5) + 2.0 * (x < -0.5 or y == 0.25)",
+              f"    parameters[{base + 2}] = np.where(x != y, x - y, 7.0)",
+              "    values[0] = 0.0 * x", "    values[1] = 0.0 * y"]
+    src = "\n".join(lines) + "\n"
+    path = tmp_path / "mm_libm_probe.py"
+    path.write_text(src)
+    spec = importlib.util.spec_from_file_location("mm_libm_probe", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(5)
+    n = 2000
+    x = rng.uniform(-1, 1, n)
+    y = rng.uniform(0.1, 1, n)
+    y[:10] = 0.25
+    x[10:20] = y[10:20]
+    m = MembraneModel(mod, None, 1, Space(np.zeros((n, 3))), verbose=False, devices=[0], n_sub=1)
+    m.set_state('V', Func(x))
+    m.set_state('w', Func(y))
+    m.step_lsoda(1.0, None)
+    got = np.asarray(m.parameters)
+    m.close()
+    pm = parse_model_source(src)
+    for r in range(0, n, 7):
+        _, want = evaluate(pm, 1.0, [x[r], y[r]], [0.0] * n_out)
+        want = np.array(want)
+        assert np.allclose(got[r], want, rtol=1e-14, atol=1e-300), (r, np.argmax(np.abs(got[r] - want)))
