@@ -105,7 +105,7 @@ def test_extra_libm_functions_and_conditionals_on_device(built, tmp_path):
              "def parameter_indices(*names):", "    return 0",
              "def rhs_numba(t, states, values, parameters):", "    x = states[0]", "    y = states[1]"]
     for k, f in enumerate(one):
-        arg = "x * 0.9" if f in ("asin", "acos") else ("x * x" if f == "log1p" else "x")
+        arg = {"asin": "x * 0.9", "acos": "x * 0.9", "log1p": "x * x", "log10": "x * x + 0.1"}.get(f, "x")
         lines.append(f"    parameters[{k}] = math.{f}({arg})")
     for k, f in enumerate(two):
         lines.append(f"    parameters[{len(one) + k}] = math.{f}(x, y)")
