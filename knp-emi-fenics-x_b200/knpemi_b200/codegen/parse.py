@@ -36,6 +36,13 @@ class ParsedModel:
     lineno: int
 
 
+def _is_values_none_guard(stmt: ast.If, values_name: str) -> bool:
+    t = stmt.test
+    return (isinstance(t, ast.Compare) and isinstance(t.left, ast.Name) and t.left.id == values_name
+            and len(t.ops) == 1 and isinstance(t.ops[0], (ast.Is, ast.IsNot))
+            and isinstance(t.comparators[0], ast.Constant) and t.comparators[0].value is None)
+
+
 def find_rhs(tree: ast.Module, func_name: str = "rhs_numba") -> ast.FunctionDef:
     found = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == func_name]
     if not found:
@@ -166,12 +173,27 @@ def parse_model_source(source: str, filename: str = "<model>", func_name: str = 
         if isinstance(stmt, ast.Expr) and isinstance(stmt.value, ast.Constant) \
                 and isinstance(stmt.value.value, str):
             continue          # docstring, or a triple-quoted block used as a comment
-        if isinstance(stmt, ast.Pass):
-            continue
-        if isinstance(stmt, ast.Return) and stmt.value is None:
+        if isinstance(stmt, (ast.Pass, ast.Assert, ast.Import, ast.ImportFrom)):
+            continue          # Gotran emits `assert(len(states) == 4)` guards
+        if isinstance(stmt, ast.Return):
             break
+        if isinstance(stmt, ast.If) and _is_values_none_guard(stmt, a_dy):
+            continue          # Gotran's `if values is None: values = np.zeros(...) else: assert ...`
+        if isinstance(stmt, ast.AugAssign) and isinstance(stmt.target, ast.Name) \
+                and type(stmt.op) in _BIN and stmt.target.id in env:
+            env[stmt.target.id] = simplify_bin(_BIN[type(stmt.op)], env[stmt.target.id], expr(stmt.value))
+            continue
         if not isinstance(stmt, ast.Assign) or len(stmt.targets) != 1:
             raise err(stmt, f"only simple assignments are supported, got {type(stmt).__name__}")
+        # `m, h, n, V = states` / `g_Na, g_K = parameters` (Gotran's unpacking of the arguments)
+        if isinstance(stmt.targets[0], (ast.Tuple, ast.List)) and isinstance(stmt.value, ast.Name) \
+                and stmt.value.id in (a_y, a_p) \
+                and all(isinstance(e, ast.Name) for e in stmt.targets[0].elts):
+            for c, e in enumerate(stmt.targets[0].elts):
+                nid = dag.state(c) if stmt.value.id == a_y else dag.param(c)
+                env[e.id] = nid
+                dag.names.setdefault(nid, e.id)
+            continue
         target = stmt.targets[0]
         nid = expr(stmt.value)
         if isinstance(target, ast.Name):

@@ -182,3 +182,33 @@ def test_conditionals_and_extra_libm_calls():
     for token in ("tanh(", "fabs(", "fmin(", "fmax(", "log1p(", "atan2(", "fmod(", "!= 0.0 ?"):
         assert token in dev, token
     assert "floor(" not in dev                     # folded constant
+
+
+def test_gotran_boilerplate_is_accepted():
+    """Unmodified Gotran output wraps the expressions in argument guards and tuple unpacking;
+    the reference authors stripped those for numba, other model files may still carry them."""
+    body = [
+        '"""Compute the right hand side"""',
+        "import math",
+        "assert(len(states) == 2)",
+        "m, V = states",
+        "assert(len(parameters) == 3)",
+        "g, E, I_out = parameters",
+        "if values is None:",
+        "    values = np.zeros((2,), dtype=np.float64)",
+        "else:",
+        "    assert isinstance(values, np.ndarray) and values.shape == (2,)",
+        "i = g * m * (V - E)",
+        "i += 0.5",
+        "parameters[2] = i",
+        "values[0] = (1 - m) * math.exp(-V / 10) - m",
+        "values[1] = -i",
+        "return values",
+    ]
+    pm = parse_model_source(_src(body))
+    dy, p_after = evaluate(pm, 0.0, [0.25, -60.0], [2.0, -80.0, 0.0])
+    import math
+    cur = 2.0 * 0.25 * (-60.0 + 80.0) + 0.5
+    assert dy == [(1 - 0.25) * math.exp(60.0 / 10) - 0.25, -cur] and p_after[2] == cur
+    em = generate_from_source(_src(body), "gotran", 2, 3)
+    assert em.out_cols == [2] and em.used_cols == [0, 1]
