@@ -380,7 +380,10 @@ class _Emitter:
         else:
             table = ""
         body = "\n".join(L).replace("@@CONST_TABLE@@", table)
-        h = hashlib.sha256(body.encode()).hexdigest()[:16]
+        # hash of the code proper: the leading "// ..." lines (generator version, options) are
+        # left out so that a generator release that emits the same code keeps the same hash
+        code = "\n".join(ln for ln in body.split("\n") if not ln.startswith("// GENERATED by"))
+        h = hashlib.sha256(code.encode()).hexdigest()[:16]
         body += (f'\nKEM_DEFINE_MODEL(Model, "{name}", "{h}", OUT_COLS, USED_COLS, {len(used_cols)})\n')
 
         def count(order, ctx):
