@@ -151,3 +151,30 @@ class _BroadcastSpace:
 
     def tabulate_dof_coordinates(self):
         return self._x
+
+
+def test_long_run_with_repeated_action_potentials(built):
+    """1000 PDE steps (100 ms) of stimulated tissue HH: four stimulus periods (mod(t, 30)), an
+    action potential in each, the stimulus cut-off at t = 125 not reached.  Round-off differences
+    between device and oracle are amplified on every upstroke; after 10^5 RK4 sub-steps per DOF
+    they are still two orders below the parity tolerance."""
+    from knpemi_b200.odeSolver import MembraneModel
+    from oracle import cpu_oracle
+    name, n, n_steps = "hh_tissue", 1000, 1000
+    ode = builtin(name)
+    S, P, X, mask = synthetic_tables(name, n, seed=31)
+    m = MembraneModel(ode, None, 1, Space(X), verbose=False, devices=[0])
+    load_tables(m, S, P)
+    P[mask, ode.parameter_indices("stim_amplitude")] = 5.0
+    v_max = np.full(n, -1e9)
+    t = 0.0
+    for k in range(n_steps):
+        m.step_async(0.1, {'stim_amplitude': 5.0}, lambda x: x[0] < 20e-6)
+        assert cpu_oracle.step(name, S, P, t, 0.1, 25, 0) == 0
+        t += 0.1
+        v_max = np.maximum(v_max, S[:, 3])
+    m.synchronize()
+    assert (v_max[mask] > 0.0).all() and (v_max[~mask] < -60.0).all()     # spikes where stimulated
+    assert close(np.asarray(m.states), S, rtol=1e-10)
+    assert close(np.asarray(m.parameters), P, rtol=1e-10)
+    m.close()
