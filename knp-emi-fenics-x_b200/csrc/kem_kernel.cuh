@@ -27,8 +27,8 @@ template <class M>
 struct KemArgs {
     long long n;
     double *y[M::NS];
-    const double *p[M::NP];
-    long long pmask[M::NP];
+    const double *p[M::NP > 0 ? M::NP : 1];      // (a model may have no parameters at all)
+    long long pmask[M::NP > 0 ? M::NP : 1];
     double *out[M::NOUT > 0 ? M::NOUT : 1];
     const unsigned char *stim_mask;
     int n_stim;
@@ -53,7 +53,7 @@ template <class M>
 __device__ __forceinline__ void kem_prologue(const KemArgs<M> &a, long long i, typename M::H &q)
 {
     constexpr int NP = M::NP;
-    double p[NP];
+    double p[NP > 0 ? NP : 1];
 #pragma unroll
     for (int c = 0; c < NP; ++c)
         p[c] = M::used(c) ? __ldg(a.p[c] + (i & a.pmask[c])) : 0.0;

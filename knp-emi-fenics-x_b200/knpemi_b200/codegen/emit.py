@@ -317,7 +317,7 @@ class _Emitter:
             w("        double unused;")
         w("    };")
         w("")
-        w("    static __device__ __forceinline__ void hoist(const double (&p)[NP], H &q)")
+        w("    static __device__ __forceinline__ void hoist(const double (&p)[NP > 0 ? NP : 1], H &q)")
         w("    {")
         L.extend(self.section(order_hoist, "hoist"))
         for nid in hoist_front:

@@ -412,3 +412,36 @@ def test_step_exchange_accepts_dlpack_host_tensors(built):
     assert np.array_equal(v_out.numpy(), b.states[:, 3])
     a.close()
     b.close()
+
+
+def test_model_without_parameters(built, tmp_path):
+    """Degenerate plugin: no parameter table at all (np = 0), one state."""
+    import importlib.util
+    src = textwrap.dedent(\'\'\'
+        import math
+        import numpy as np
+        def init_state_values(**values):
+            return np.array([1.0], dtype=np.float64)
+        def init_parameter_values(**values):
+            return np.array([], dtype=np.float64)
+        def state_indices(*names):
+            return 0
+        def parameter_indices(*names):
+            raise ValueError("Unknown param: '{0}'".format(names[0]))
+        def rhs_numba(t, states, values, parameters):
+            values[0] = -2.0 * states[0]
+    \'\'\')
+    path = tmp_path / "mm_decay.py"
+    path.write_text(src)
+    spec = importlib.util.spec_from_file_location("mm_decay", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from knpemi_b200.odeSolver import MembraneModel
+    m = MembraneModel(mod, None, 1, Space(np.zeros((300, 3))), verbose=False, devices=[0])
+    assert m.parameters.shape == (300, 0) and m.output_columns == []
+    for _ in range(10):
+        m.step_lsoda(0.05, None)
+    assert np.allclose(np.asarray(m.states)[:, 0], np.exp(-1.0), rtol=1e-9)
+    with pytest.raises(ValueError):
+        m.step_lsoda(0.05, {'stim_amplitude': 1.0})
+    m.close()
