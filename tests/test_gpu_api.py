@@ -417,7 +417,7 @@ def test_step_exchange_accepts_dlpack_host_tensors(built):
 def test_model_without_parameters(built, tmp_path):
     """Degenerate plugin: no parameter table at all (np = 0), one state."""
     import importlib.util
-    src = textwrap.dedent(\'\'\'
+    src = textwrap.dedent('''
         import math
         import numpy as np
         def init_state_values(**values):
@@ -430,7 +430,7 @@ def test_model_without_parameters(built, tmp_path):
             raise ValueError("Unknown param: '{0}'".format(names[0]))
         def rhs_numba(t, states, values, parameters):
             values[0] = -2.0 * states[0]
-    \'\'\')
+    ''')
     path = tmp_path / "mm_decay.py"
     path.write_text(src)
     spec = importlib.util.spec_from_file_location("mm_decay", path)
