@@ -47,7 +47,6 @@ class kem_io_column(C.Structure):
 
 
 _DP = C.POINTER(C.c_double)
-_U8P = C.POINTER(C.c_uint8)
 _IP = C.POINTER(C.c_int)
 _H = C.c_void_p
 
@@ -150,12 +149,6 @@ def model_info(model_id: int) -> kem_model_info:
     info = kem_model_info()
     check(lib().kem_model_get_info(model_id, C.byref(info)), "kem_model_get_info")
     return info
-
-
-def ptr(a: np.ndarray) -> int:
-    """Raw data pointer of a C-contiguous array (caller keeps it alive)."""
-    assert a.flags.c_contiguous
-    return a.ctypes.data
 
 
 def _free_pinned(ptr: int):

@@ -14,7 +14,8 @@ What differs, deliberately (SURVEY.md sections 0 and 8):
 * the per-row LSODA solve (odeSolver.py:116-120; numbalsoda, un-pinned) is replaced
   by the fixed-step scheme O1: classical RK4 with ``n_sub`` sub-steps (default 25,
   the reference's vestigial ``n_steps_ODE``, run_2D.py:176) and the channel currents
-  evaluated at ``(t+dt, y(t+dt))``;
+  evaluated at ``(t+dt, y(t+dt))``; ``scheme="dp45"`` selects the error-controlled scheme
+  O3 (Dormand-Prince 5(4) at the reference's LSODA tolerances) instead;
 * model defaults are read once instead of N times (odeSolver.py:41-42), locator
   masks are evaluated vectorised when that provably gives the per-row answer, and
   cached per callable.
@@ -269,8 +270,9 @@ class MembraneModel:
     def step_lsoda(self, dt, stimulus, stimulus_locator=None):
         '''Solve the ODEs forward by dt with optional stimulus.
 
-        Kept under the reference's name so `solve_odes` (run_2D.py:98) is
-        untouched; the integrator is the fixed-step scheme of :meth:`step`.'''
+        Kept under the reference's name so `solve_odes` (run_2D.py:98) is untouched; the
+        integrator is the scheme chosen at construction (`scheme="rk4"`: fixed-step O1, the
+        default; `scheme="dp45"`: error-controlled O3), see :meth:`step`.'''
         return self.step(dt, stimulus, stimulus_locator)
 
     def step(self, dt, stimulus=None, stimulus_locator=None, n_sub=None, timed=False):
