@@ -488,16 +488,21 @@ int prepare_step(kem_handle h, double t0, double dt, int n_sub, int scheme, int 
     pl.n_sub = scheme == KEM_SCHEME_RK4 ? n_sub : 0;
     pl.hstep = scheme == KEM_SCHEME_RK4 ? dt / (double)n_sub : 0.0;
     if (scheme == KEM_SCHEME_DP45)
-        for (Shard &s : h->shards) {
-            if (s.d_hsug) continue;
+        for (Shard &s : h->shards) {      // per-DOF step sizes, counters, activity sort buffers
             CK(cudaSetDevice(s.dev));
-            CK(cudaMalloc(&s.d_hsug, std::max<size_t>((size_t)s.n, 1) * sizeof(double)));
-            CK(cudaMemsetAsync(s.d_hsug, 0, std::max<size_t>((size_t)s.n, 1) * sizeof(double), s.stream));
-            CK(cudaMalloc(&s.d_stats, 2 * sizeof(unsigned long long)));
-            CK(cudaMemsetAsync(s.d_stats, 0, 2 * sizeof(unsigned long long), s.stream));
-            CK(cudaHostAlloc((void **)&s.h_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
-            CK(cudaMalloc(&s.d_perm, std::max<size_t>((size_t)s.n, 1) * sizeof(int)));
-            CK(cudaMalloc(&s.d_act, (2 * ACT_BUCKETS + 1) * sizeof(unsigned)));
+            const size_t nn = std::max<size_t>((size_t)s.n, 1);
+            if (!s.d_hsug) {
+                CK(cudaMalloc(&s.d_hsug, nn * sizeof(double)));
+                CK(cudaMemsetAsync(s.d_hsug, 0, nn * sizeof(double), s.stream));
+            }
+            if (!s.d_stats) {
+                CK(cudaMalloc(&s.d_stats, 2 * sizeof(unsigned long long)));
+                CK(cudaMemsetAsync(s.d_stats, 0, 2 * sizeof(unsigned long long), s.stream));
+            }
+            if (!s.h_stats)
+                CK(cudaHostAlloc((void **)&s.h_stats, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+            if (!s.d_perm) CK(cudaMalloc(&s.d_perm, nn * sizeof(int)));
+            if (!s.d_act) CK(cudaMalloc(&s.d_act, (2 * ACT_BUCKETS + 1) * sizeof(unsigned)));
         }
     pl.masked = !h->shards.empty() && h->shards[0].has_mask;
     for (int s = 0; s < n_stim; ++s) {
