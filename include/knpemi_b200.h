@@ -105,6 +105,12 @@ int kem_get_column(kem_handle h, int kind, int col, double *host_dst, int64_t n)
 /* 1 if the column is stored as one value for all DOFs */
 int kem_column_is_uniform(kem_handle h, int kind, int col, int *is_uniform_out, double *value_out);
 
+/* where a column currently lives: 0 = one value for all DOFs, 1 = per-DOF column in HBM,
+ * 2 = per-DOF host shadow.  A parameter slot the generated right-hand side neither reads nor
+ * writes (for the HH models: Cl_e, Cl_i) is kept on the host by kem_set_column / kem_step_io --
+ * it is uploaded only if a masked setter, a device gather/scatter or a stimulus needs it there. */
+int kem_column_location(kem_handle h, int kind, int col, int *location_out);
+
 /* ---- stimulus mask: `stimulus_mask` of step_lsoda (odeSolver.py:98-100) ------- */
 /* Upload the 0/1 mask used by the next kem_step calls; NULL = every DOF (the
  * reference's default locator `lambda x: True`). */

@@ -276,6 +276,12 @@ struct kem_handle_s {
     std::vector<Shard> shards;
     std::vector<double> uni;          // np: value of uniform parameter columns
     std::vector<char> p_uniform;      // np: 1 = stored as one value
+    // Parameter slots the generated right-hand side never reads (HH: Cl_e, Cl_i; the I_ch_*
+    // inputs) need not travel to the GPU at all: a full-column write to such a slot is kept
+    // in a host shadow (p_host = 1) and only uploaded if something on the device asks for it.
+    std::vector<char> p_dead;         // np: 1 = neither read nor written by the RHS
+    std::vector<char> p_host;         // np: 1 = current value lives in p_shadow, not on the device
+    std::vector<std::vector<double>> p_shadow;
     bool uni_dirty = true;
     int block = 0;
     int64_t launches = 0;
@@ -387,6 +393,13 @@ int small_upload(Shard &s, void *dst, const void *src, size_t bytes)
     return KEM_OK;
 }
 
+// true if the parameter column's current value is not in a per-DOF device column
+bool not_on_device(kem_handle h, int col)
+{
+    return h->p_uniform[col] || h->p_host[col] || (!h->shards.empty() && !h->shards[0].pcol[col]);
+}
+
+// make the parameter column a per-DOF device column holding its current value
 int ensure_pcol(kem_handle h, int col)
 {
     for (Shard &s : h->shards) {
@@ -397,10 +410,27 @@ int ensure_pcol(kem_handle h, int col)
             k_fill<<<grid_for(s.n), 256, 0, s.stream>>>(s.pcol[col], s.n, h->uni[col]);
             CK(cudaGetLastError());
             h->launches++;
+        } else if (h->p_host[col] && s.n > 0) {
+            int rc = copy_in(s, s.pcol[col], h->p_shadow[col].data() + s.begin, (size_t)s.n * sizeof(double),
+                             s.stream, false);
+            if (rc) return rc;
         }
     }
     h->p_uniform[col] = 0;
+    if (h->p_host[col]) {
+        h->p_host[col] = 0;
+        std::vector<double>().swap(h->p_shadow[col]);
+    }
     return KEM_OK;
+}
+
+// full-column write to a parameter slot the RHS never touches: host shadow only
+void shadow_store(kem_handle h, int col, const double *src)
+{
+    h->p_shadow[col].resize((size_t)h->n);
+    CopyPool::get().copy(h->p_shadow[col].data(), src, (size_t)h->n * sizeof(double));
+    h->p_uniform[col] = 0;
+    h->p_host[col] = 1;
 }
 
 int check_col(kem_handle h, int kind, int col, const char *fn)
@@ -511,7 +541,7 @@ int prepare_step(kem_handle h, double t0, double dt, int n_sub, int scheme, int 
             pl.stim_col[pl.n_stim] = stim_cols[s];
             pl.stim_val[pl.n_stim] = stim_vals[s];
             pl.n_stim++;
-            if (h->p_uniform[stim_cols[s]]) {
+            if (not_on_device(h, stim_cols[s])) {
                 int rc = ensure_pcol(h, stim_cols[s]);
                 if (rc) return rc;
             }
@@ -573,7 +603,7 @@ int launch_range(kem_handle h, Shard &s, const StepPlan &pl, int64_t off, int64_
     std::vector<double *> o(std::max(m->n_out, 1));
     for (int c = 0; c < m->ns; ++c) y[c] = s.ycol[c] + off;
     for (int c = 0; c < m->np; ++c) {
-        if (h->p_uniform[c]) {
+        if (h->p_uniform[c] || h->p_host[c]) {      // (a host-shadowed slot is never read by the kernel)
             p[c] = s.d_uni + c;
             pm[c] = 0;
         } else {
@@ -773,6 +803,12 @@ int kem_create(int model_id, int64_t n_dof, int n_dev, const int *dev_ids,
     h->n = n_dof;
     h->uni.assign(param_defaults, param_defaults + m->np);
     h->p_uniform.assign(m->np, 1);
+    h->p_host.assign(m->np, 0);
+    h->p_shadow.resize(m->np);
+    h->p_dead.assign(m->np, 1);
+    for (int k = 0; k < m->n_used; ++k) h->p_dead[m->used_cols[k]] = 0;
+    for (int k = 0; k < m->n_out; ++k) h->p_dead[m->out_cols[k]] = 0;
+    if (getenv("KNPEMI_NO_HOST_SHADOW")) h->p_dead.assign(m->np, 0);
     h->shards.resize(n_dev);
     const int64_t per = (n_dof + n_dev - 1) / n_dev;   // contiguous ranges, remainder on the last
     auto bail = [&](int rc) {
@@ -912,6 +948,7 @@ int kem_set_uniform(kem_handle h, int kind, int col, double v)
         if (h->p_uniform[col] && memcmp(&h->uni[col], &v, sizeof v) == 0) return KEM_OK;
         h->uni[col] = v;
         h->p_uniform[col] = 1;
+        h->p_host[col] = 0;
         h->uni_dirty = true;
         return KEM_OK;
     }
@@ -933,13 +970,18 @@ int kem_set_column(kem_handle h, int kind, int col, const double *src, int64_t n
     if (rc) return rc;
     ARG(n == h->n, "length must equal the handle's n_dof");
     ARG(src || n == 0, "null source");
-    if (kind == KEM_PARAM && (h->p_uniform[col] || !h->shards[0].pcol[col])) {
+    if (kind == KEM_PARAM && h->p_dead[col] && n > 0) {
+        shadow_store(h, col, src);
+        return KEM_OK;
+    }
+    if (kind == KEM_PARAM && not_on_device(h, col)) {
         // becomes a per-DOF column; no need to pre-fill, every row is overwritten
         for (Shard &s : h->shards) {
             CK(cudaSetDevice(s.dev));
             if (!s.pcol[col] && s.n > 0) CK(cudaMalloc(&s.pcol[col], (size_t)s.n * sizeof(double)));
         }
         h->p_uniform[col] = 0;
+        h->p_host[col] = 0;
     }
     const bool pinned = n > 0 && is_pinned(src);
     for (Shard &s : h->shards) {
@@ -979,7 +1021,7 @@ int kem_set_column_masked(kem_handle h, int kind, int col, const double *src,
     if (rc) return rc;
     ARG(n == h->n, "length must equal the handle's n_dof");
     ARG((src && host_mask) || n == 0, "null source or mask");
-    if (kind == KEM_PARAM && h->p_uniform[col]) {
+    if (kind == KEM_PARAM && not_on_device(h, col)) {
         rc = ensure_pcol(h, col);
         if (rc) return rc;
     }
@@ -1007,7 +1049,7 @@ int kem_set_value_masked(kem_handle h, int kind, int col, double v, const uint8_
     if (rc) return rc;
     ARG(n == h->n, "length must equal the handle's n_dof");
     ARG(host_mask || n == 0, "null mask");
-    if (kind == KEM_PARAM && h->p_uniform[col]) {
+    if (kind == KEM_PARAM && not_on_device(h, col)) {
         rc = ensure_pcol(h, col);
         if (rc) return rc;
     }
@@ -1036,6 +1078,10 @@ int kem_get_column(kem_handle h, int kind, int col, double *dst, int64_t n)
         std::fill(dst, dst + n, h->uni[col]);
         return KEM_OK;
     }
+    if (kind == KEM_PARAM && h->p_host[col]) {
+        CopyPool::get().copy(dst, h->p_shadow[col].data(), (size_t)n * sizeof(double));
+        return KEM_OK;
+    }
     const bool pinned = n > 0 && is_pinned(dst);
     for (Shard &s : h->shards) {
         rc = copy_out(s, dst + s.begin, col_ptr(s, kind, col), (size_t)s.n * sizeof(double), s.stream,
@@ -1058,6 +1104,16 @@ int kem_column_is_uniform(kem_handle h, int kind, int col, int *is_uniform_out, 
     const bool u = kind == KEM_PARAM && h->p_uniform[col];
     *is_uniform_out = u ? 1 : 0;
     if (value_out) *value_out = u ? h->uni[col] : 0.0;
+    return KEM_OK;
+}
+
+int kem_column_location(kem_handle h, int kind, int col, int *location_out)
+{
+    int rc = check_col(h, kind, col, __func__);
+    if (rc) return rc;
+    ARG(location_out, "null output");
+    if (kind == KEM_STATE) *location_out = 1;
+    else *location_out = h->p_uniform[col] ? 0 : (h->p_host[col] ? 2 : 1);
     return KEM_OK;
 }
 
@@ -1129,18 +1185,27 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
     ARG(n_in >= 0 && n_out >= 0 && (in || !n_in) && (out || !n_out), "bad io arrays");
     int rc;
     bool all_pinned = true;
+    // columns that really cross the host link; inputs to slots the RHS never reads stay in
+    // their host shadow, outputs that live in a host shadow are copied from it
+    std::vector<kem_io_column> dev_in, dev_out, shadow_in, shadow_out;
     for (int k = 0; k < n_in; ++k) {
         rc = check_col(h, in[k].kind, in[k].col, __func__);
         if (rc) return rc;
         ARG(in[k].host || h->n == 0, "null input column");
+        if (in[k].kind == KEM_PARAM && h->p_dead[in[k].col] && h->n > 0) {
+            shadow_in.push_back(in[k]);
+            continue;
+        }
+        dev_in.push_back(in[k]);
         all_pinned = all_pinned && (h->n == 0 || is_pinned(in[k].host));
-        if (in[k].kind == KEM_PARAM && (h->p_uniform[in[k].col] || !h->shards[0].pcol[in[k].col])) {
+        if (in[k].kind == KEM_PARAM && not_on_device(h, in[k].col)) {
             for (Shard &s : h->shards) {
                 CK(cudaSetDevice(s.dev));
                 if (!s.pcol[in[k].col] && s.n > 0)
                     CK(cudaMalloc(&s.pcol[in[k].col], (size_t)s.n * sizeof(double)));
             }
             h->p_uniform[in[k].col] = 0;
+            h->p_host[in[k].col] = 0;
         }
     }
     for (int k = 0; k < n_out; ++k) {
@@ -1149,8 +1214,26 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
         ARG(out[k].host || h->n == 0, "null output column");
         ARG(!(out[k].kind == KEM_PARAM && h->p_uniform[out[k].col]),
             "output column is uniform; read it with kem_get_column");
+        bool from_shadow = out[k].kind == KEM_PARAM && h->p_host[out[k].col];
+        for (const kem_io_column &c : shadow_in)
+            from_shadow = from_shadow || (out[k].kind == KEM_PARAM && c.col == out[k].col);
+        if (from_shadow) {
+            shadow_out.push_back(out[k]);
+            continue;
+        }
+        dev_out.push_back(out[k]);
         all_pinned = all_pinned && (h->n == 0 || is_pinned(out[k].host));
     }
+    in = dev_in.data();
+    n_in = (int)dev_in.size();
+    out = dev_out.data();
+    n_out = (int)dev_out.size();
+    // host-side part of the exchange; runs while the devices work (the calls below only enqueue)
+    auto host_side = [&]() {
+        for (const kem_io_column &c : shadow_in) shadow_store(h, c.col, c.host);
+        for (const kem_io_column &c : shadow_out)
+            CopyPool::get().copy(c.host, h->p_shadow[c.col].data(), (size_t)h->n * sizeof(double));
+    };
     StepPlan pl;
     rc = prepare_step(h, t0, dt, n_sub, scheme, n_stim, stim_cols, stim_vals, pl);
     if (rc) return rc;
@@ -1170,6 +1253,7 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
             if (rc) return rc;
             CK(cudaEventRecord(s.ev_c, s.stream));
         }
+        host_side();
         for (Shard &s : h->shards) {
             for (int k = 0; k < n_out; ++k) {
                 rc = copy_out(s, out[k].host + s.begin, col_ptr(s, out[k].kind, out[k].col),
@@ -1237,6 +1321,7 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
         // later work on `stream` (the next step) must not overtake the D2H copies
         CK(cudaStreamWaitEvent(s.stream, s.io_out[n_chunks - 1], 0));
     }
+    host_side();
     if (times) memset(times, 0, sizeof *times);
     for (Shard &s : h->shards) {
         if (s.n == 0) continue;
@@ -1384,7 +1469,7 @@ int kem_device_gather(kem_handle h, int shard, int kind, int col, const double *
 {
     int rc = device_xfer_check(h, shard, kind, col, dev_src, map_id, __func__);
     if (rc) return rc;
-    if (kind == KEM_PARAM && (h->p_uniform[col] || !h->shards[0].pcol[col])) {
+    if (kind == KEM_PARAM && not_on_device(h, col)) {
         rc = ensure_pcol(h, col);
         if (rc) return rc;
     }
@@ -1404,8 +1489,8 @@ int kem_device_scatter(kem_handle h, int shard, int kind, int col, double *dev_d
     Shard &s = h->shards[shard];
     if (s.n == 0) return KEM_OK;
     CK(cudaSetDevice(s.dev));
-    if (kind == KEM_PARAM && h->p_uniform[col]) {
-        rc = ensure_pcol(h, col);       // materialise the uniform value as a column first
+    if (kind == KEM_PARAM && not_on_device(h, col)) {
+        rc = ensure_pcol(h, col);       // materialise a uniform / host-shadowed value as a column first
         if (rc) return rc;
     }
     k_scatter<<<grid_for(s.n), 256, 0, s.stream>>>(dev_dst, col_ptr(s, kind, col), s.d_map[map_id], s.n);
@@ -1422,7 +1507,7 @@ int kem_device_gather_diff(kem_handle h, int shard, int kind, int col, const dou
     if (rc) return rc;
     rc = device_xfer_check(h, shard, kind, col, dev_b, map_b, __func__);
     if (rc) return rc;
-    if (kind == KEM_PARAM && (h->p_uniform[col] || !h->shards[0].pcol[col])) {
+    if (kind == KEM_PARAM && not_on_device(h, col)) {
         rc = ensure_pcol(h, col);
         if (rc) return rc;
     }
@@ -1441,7 +1526,7 @@ int kem_device_copy_in(kem_handle h, int shard, int kind, int col, const double 
     int rc = check_col(h, kind, col, __func__);
     if (rc) return rc;
     ARG(shard >= 0 && shard < (int)h->shards.size(), "shard out of range");
-    if (kind == KEM_PARAM && (h->p_uniform[col] || !h->shards[0].pcol[col])) {
+    if (kind == KEM_PARAM && not_on_device(h, col)) {
         rc = ensure_pcol(h, col);
         if (rc) return rc;
     }
@@ -1459,7 +1544,7 @@ int kem_device_copy_out(kem_handle h, int shard, int kind, int col, double *dev_
     int rc = check_col(h, kind, col, __func__);
     if (rc) return rc;
     ARG(shard >= 0 && shard < (int)h->shards.size(), "shard out of range");
-    if (kind == KEM_PARAM && h->p_uniform[col]) {
+    if (kind == KEM_PARAM && not_on_device(h, col)) {
         rc = ensure_pcol(h, col);
         if (rc) return rc;
     }

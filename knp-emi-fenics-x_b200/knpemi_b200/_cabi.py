@@ -69,6 +69,7 @@ SIGNATURES = {
     "kem_set_value_masked": (C.c_int, [_H, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int64]),
     "kem_get_column": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p, C.c_int64]),
     "kem_column_is_uniform": (C.c_int, [_H, C.c_int, C.c_int, _IP, _DP]),
+    "kem_column_location": (C.c_int, [_H, C.c_int, C.c_int, _IP]),
     "kem_set_stimulus_mask": (C.c_int, [_H, C.c_void_p, C.c_int64]),
     "kem_step": (C.c_int, [_H, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _IP, _DP, _IP]),
     "kem_step_timed": (C.c_int, [_H, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _IP, _DP, _IP,

@@ -432,6 +432,14 @@ class MembraneModel:
         check(self._lib.kem_get_step_stats(self._h, C.byref(a), C.byref(r)), "kem_get_step_stats")
         return a.value, r.value
 
+    def column_location(self, what, which):
+        '''"uniform" | "device" | "host": where the column currently lives (a parameter the
+        right-hand side never touches stays in a host shadow).'''
+        kind, col = self._kind_col(what, which)
+        loc = C.c_int(-1)
+        check(self._lib.kem_column_location(self._h, kind, col, C.byref(loc)), "kem_column_location")
+        return ("uniform", "device", "host")[loc.value]
+
     def launch_count(self):
         n = C.c_int64(0)
         check(self._lib.kem_launch_count(self._h, C.byref(n)), "kem_launch_count")

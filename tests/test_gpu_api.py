@@ -445,3 +445,46 @@ def test_model_without_parameters(built, tmp_path):
     with pytest.raises(ValueError):
         m.step_lsoda(0.05, {'stim_amplitude': 1.0})
     m.close()
+
+
+def test_parameters_the_rhs_never_reads_stay_on_the_host(built):
+    """HH never reads Cl_e / Cl_i (mm_hh.py assigns them to unused locals): full-column writes to
+    such slots are kept in a host shadow, every API path still sees the values."""
+    gpu, cpu, X, rng = make_pair("hh_tissue", 4001, devices=[0, 0])
+    n = 4001
+    cl_e, cl_i, k_e = rng.normal(size=n), rng.normal(size=n), 3.0 + rng.normal(size=n) * 0.01
+    for m in (gpu, cpu):
+        m.set_parameter('Cl_e', Func(cl_e))
+        m.set_parameter('K_e', Func(k_e))
+    assert gpu.column_location('parameter', 'Cl_e') == "host"
+    assert gpu.column_location('parameter', 'K_e') == "device"
+    assert gpu.column_location('parameter', 'Cm') == "uniform"
+    # reads, masked writes (forces the upload), value setters
+    loc = lambda x: x[0] < 30e-6      # noqa: E731
+    for m in (gpu, cpu):
+        m.set_parameter('Cl_e', Func(cl_i), locator=loc)
+        m.set_parameter_values({'Cl_i': lambda x: x[1] * 1e3}, locator=loc)
+        m.set_parameter('Cl_i', Func(cl_e))                         # full write again: back to the shadow
+    assert gpu.column_location('parameter', 'Cl_e') == "device"
+    assert gpu.column_location('parameter', 'Cl_i') == "host"
+    for name in ('Cl_e', 'Cl_i', 'K_e'):
+        a, b = Func(np.zeros(n)), Func(np.zeros(n))
+        gpu.get_parameter(name, a)
+        cpu.get_parameter(name, b)
+        assert np.array_equal(a.x.array, b.x.array), name
+    # through the pipelined exchange, as input and as output
+    from knpemi_b200._cabi import pinned_empty
+    buf_in, buf_out, v_out = pinned_empty(n), pinned_empty(n), pinned_empty(n)
+    buf_in[:] = rng.normal(size=n)
+    cfg = SETUP["hh_tissue"]
+    for m in (gpu, cpu):
+        for k, v in {**cfg["uniform"], **{kk: vv for kk, vv in cfg["varying"].items() if kk != 'K_e'}}.items():
+            if not k.startswith("Cl"):
+                m.set_parameter_values({k: lambda x, v=v: v})
+    gpu.step_exchange(0.1, {("parameter", "Cl_e"): buf_in}, {("parameter", "Cl_e"): buf_out, ("state", "V"): v_out})
+    cpu.set_parameter('Cl_e', Func(np.array(buf_in)))
+    cpu.step_lsoda(0.1, None)
+    assert np.array_equal(buf_out, buf_in) and gpu.column_location('parameter', 'Cl_e') == "host"
+    assert close(np.asarray(gpu.states), cpu.states)
+    assert np.array_equal(np.asarray(gpu.parameters)[:, 13:15], cpu.parameters[:, 13:15])
+    gpu.close()
