@@ -235,6 +235,8 @@ struct Shard {
     int dev = 0;
     int64_t begin = 0, n = 0;
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaStream_t stream2 = nullptr;   // second compute stream: chunk kernels of kem_step_io alternate
+                                      // between the two so one chunk's tail overlaps the next one's head
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // kem_timer_begin / kem_timer_end
     std::vector<double *> ycol;   // ns per-DOF state columns
@@ -449,6 +451,7 @@ int sync_all(kem_handle h)
     for (Shard &s : h->shards) {
         CK(cudaSetDevice(s.dev));
         CK(cudaStreamSynchronize(s.s_in));
+        CK(cudaStreamSynchronize(s.stream2));
         CK(cudaStreamSynchronize(s.stream));
         CK(cudaStreamSynchronize(s.s_out));
     }
@@ -594,8 +597,10 @@ int build_activity_perm(kem_handle h, Shard &s, double dt)
 }
 
 // enqueue the fused kernel for DOFs [off, off+len) of shard s on its compute stream
-int launch_range(kem_handle h, Shard &s, const StepPlan &pl, int64_t off, int64_t len)
+int launch_range(kem_handle h, Shard &s, const StepPlan &pl, int64_t off, int64_t len,
+                 cudaStream_t on = nullptr)
 {
+    if (!on) on = s.stream;
     const KemModelDesc *m = h->m;
     std::vector<double *> y(m->ns);
     std::vector<const double *> p(m->np);
@@ -650,7 +655,7 @@ int launch_range(kem_handle h, Shard &s, const StepPlan &pl, int64_t off, int64_
         }
     }
     CK(cudaSetDevice(s.dev));
-    cudaError_t e = m->launch(&L, s.stream);
+    cudaError_t e = m->launch(&L, on);
     if (e != cudaSuccess)
         return fail(KEM_E_CUDA, std::string("step kernel launch failed: ") + cudaGetErrorString(e));
     h->launches++;
@@ -839,6 +844,7 @@ int kem_create(int model_id, int64_t n_dof, int n_dev, const int *dev_ids,
         CKB(cudaSetDevice(s.dev));
         CKB(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CKB(cudaStreamCreateWithFlags(&s.s_in, cudaStreamNonBlocking));
+        CKB(cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
         CKB(cudaStreamCreateWithFlags(&s.s_out, cudaStreamNonBlocking));
         CKB(cudaEventCreate(&s.ev_a));
         CKB(cudaEventCreate(&s.ev_b));
@@ -884,6 +890,7 @@ int kem_destroy(kem_handle h)
         if (cudaSetDevice(s.dev) != cudaSuccess) continue;
         if (s.stream) cudaStreamSynchronize(s.stream);
         if (s.s_in) cudaStreamSynchronize(s.s_in);
+        if (s.stream2) cudaStreamSynchronize(s.stream2);
         if (s.s_out) cudaStreamSynchronize(s.s_out);
         for (double *p : s.ycol) if (p) cudaFree(p);
         for (double *p : s.pcol) if (p) cudaFree(p);
@@ -911,6 +918,7 @@ int kem_destroy(kem_handle h)
         for (cudaEvent_t e : {s.ev_a, s.ev_b, s.ev_c, s.ev_d, s.ev_t0, s.ev_t1}) if (e) cudaEventDestroy(e);
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.s_in) cudaStreamDestroy(s.s_in);
+        if (s.stream2) cudaStreamDestroy(s.stream2);
         if (s.s_out) cudaStreamDestroy(s.s_out);
     }
     cudaGetLastError();
@@ -1299,7 +1307,9 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
         // the copy streams must see the table/uniform uploads and earlier work on `stream`
         CK(cudaEventRecord(s.ev_a, s.stream));
         CK(cudaStreamWaitEvent(s.s_in, s.ev_a, 0));
+        CK(cudaStreamWaitEvent(s.stream2, s.ev_a, 0));
         CK(cudaEventRecord(s.ev_b, s.s_in));   // t = 0 of this shard's exchange
+        const bool two = getenv("KNPEMI_IO_ONE_COMPUTE_STREAM") == nullptr;
         for (int c = 0; c < n_chunks; ++c) {
             const int64_t off = (int64_t)c * chunk;
             const int64_t len = std::min(chunk, s.n - off);
@@ -1307,11 +1317,12 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
                 CK(cudaMemcpyAsync(col_ptr(s, in[k].kind, in[k].col) + off, in[k].host + s.begin + off,
                                    (size_t)len * sizeof(double), cudaMemcpyHostToDevice, s.s_in));
             CK(cudaEventRecord(s.io_in[c], s.s_in));
-            CK(cudaStreamWaitEvent(s.stream, s.io_in[c], 0));
-            CK(cudaEventRecord(s.io_k0[c], s.stream));
-            rc = launch_range(h, s, pl, off, len);
+            cudaStream_t sk = (two && (c & 1)) ? s.stream2 : s.stream;
+            CK(cudaStreamWaitEvent(sk, s.io_in[c], 0));
+            CK(cudaEventRecord(s.io_k0[c], sk));
+            rc = launch_range(h, s, pl, off, len, sk);
             if (rc) return rc;
-            CK(cudaEventRecord(s.io_k1[c], s.stream));
+            CK(cudaEventRecord(s.io_k1[c], sk));
             CK(cudaStreamWaitEvent(s.s_out, s.io_k1[c], 0));
             for (int k = 0; k < n_out; ++k)
                 CK(cudaMemcpyAsync(out[k].host + s.begin + off, col_ptr(s, out[k].kind, out[k].col) + off,
