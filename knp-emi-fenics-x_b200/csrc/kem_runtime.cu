@@ -284,6 +284,7 @@ struct kem_handle_s {
     std::vector<char> p_dead;         // np: 1 = neither read nor written by the RHS
     std::vector<char> p_host;         // np: 1 = current value lives in p_shadow, not on the device
     std::vector<std::vector<double>> p_shadow;
+    bool shadow_pinned_io = true;     // kem_step_io: pinned inputs to dead slots go to the shadow too
     bool uni_dirty = true;
     int block = 0;
     int64_t launches = 0;
@@ -424,6 +425,20 @@ int ensure_pcol(kem_handle h, int col)
         std::vector<double>().swap(h->p_shadow[col]);
     }
     return KEM_OK;
+}
+
+// Where kem_step_io puts a PINNED input to a slot the RHS never touches.  The shadow copy
+// replaces one DMA read of the column by a host read + write of it.  With one or two GPUs
+// on the host the link is the bottleneck and the shadow wins (1 GPU: 10.9 vs 12.9 ms per
+// exchange of 1e7 DOFs); with four or more the host memory system is, and the DMA wins
+// (4 GPUs, same box: 2.02e9 vs 1.70e9 DOF-steps/s; profiles/r1_bench.md).  Pageable inputs
+// always go to the shadow: their alternative is a staging copy plus the DMA.
+bool shadow_pinned_inputs(int n_dev)
+{
+    if (const char *e = getenv("KNPEMI_HOST_SHADOW_IO")) return atoi(e) != 0;
+    int sharing = n_dev;                                   // GPUs fed from this host's memory
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) sharing = std::max(sharing, n_dev * atoi(e));
+    return sharing <= 2;
 }
 
 // full-column write to a parameter slot the RHS never touches: host shadow only
@@ -814,6 +829,7 @@ int kem_create(int model_id, int64_t n_dof, int n_dev, const int *dev_ids,
     for (int k = 0; k < m->n_used; ++k) h->p_dead[m->used_cols[k]] = 0;
     for (int k = 0; k < m->n_out; ++k) h->p_dead[m->out_cols[k]] = 0;
     if (getenv("KNPEMI_NO_HOST_SHADOW")) h->p_dead.assign(m->np, 0);
+    h->shadow_pinned_io = shadow_pinned_inputs(n_dev);
     h->shards.resize(n_dev);
     const int64_t per = (n_dof + n_dev - 1) / n_dev;   // contiguous ranges, remainder on the last
     auto bail = [&](int rc) {
@@ -1200,7 +1216,8 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
         rc = check_col(h, in[k].kind, in[k].col, __func__);
         if (rc) return rc;
         ARG(in[k].host || h->n == 0, "null input column");
-        if (in[k].kind == KEM_PARAM && h->p_dead[in[k].col] && h->n > 0) {
+        if (in[k].kind == KEM_PARAM && h->p_dead[in[k].col] && h->n > 0 &&
+            (h->shadow_pinned_io || !is_pinned(in[k].host))) {
             shadow_in.push_back(in[k]);
             continue;
         }
@@ -1214,6 +1231,7 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
             }
             h->p_uniform[in[k].col] = 0;
             h->p_host[in[k].col] = 0;
+            std::vector<double>().swap(h->p_shadow[in[k].col]);
         }
     }
     for (int k = 0; k < n_out; ++k) {

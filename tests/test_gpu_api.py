@@ -488,3 +488,33 @@ def test_parameters_the_rhs_never_reads_stay_on_the_host(built):
     assert close(np.asarray(gpu.states), cpu.states)
     assert np.array_equal(np.asarray(gpu.parameters)[:, 13:15], cpu.parameters[:, 13:15])
     gpu.close()
+
+
+def test_exchange_uploads_unread_pinned_inputs_when_the_host_is_shared(built, monkeypatch):
+    """With more than two GPUs fed from one host, kem_step_io sends pinned inputs to unread slots
+    over the link instead of through a host copy (csrc/kem_runtime.cu:shadow_pinned_inputs);
+    the values every getter sees are the same either way, pageable inputs still use the shadow."""
+    from knpemi_b200._cabi import pinned_empty
+    n = 3000
+    seen = {}
+    for policy, local_world in (("shadow", "1"), ("upload", "4")):
+        monkeypatch.setenv("LOCAL_WORLD_SIZE", local_world)
+        gpu, cpu, X, rng = make_pair("hh_ideal", n, devices=[0])
+        cfg = SETUP["hh_ideal"]
+        for k, v in {**cfg["uniform"], **cfg["varying"]}.items():
+            gpu.set_parameter_values({k: lambda x, v=v: v})
+        cl_e, cl_i, v_out, cl_back = pinned_empty(n), rng.normal(size=n), pinned_empty(n), pinned_empty(n)
+        cl_e[:] = rng.normal(size=n)
+        gpu.step_exchange(cfg["dt"], {("parameter", "Cl_e"): cl_e, ("parameter", "Cl_i"): cl_i},
+                          {("state", "V"): v_out})
+        assert gpu.column_location('parameter', 'Cl_e') == ("host" if policy == "shadow" else "device")
+        assert gpu.column_location('parameter', 'Cl_i') == "host"          # pageable: always the shadow
+        gpu.step_exchange(cfg["dt"], {("parameter", "Cl_e"): cl_e}, {("state", "V"): v_out, ("parameter", "Cl_e"): cl_back})
+        assert np.array_equal(cl_back, cl_e)
+        a, b = Func(np.zeros(n)), Func(np.zeros(n))
+        gpu.get_parameter('Cl_e', a)
+        gpu.get_parameter('Cl_i', b)
+        assert np.array_equal(a.x.array, cl_e) and np.array_equal(b.x.array, cl_i)
+        seen[policy] = np.array(v_out)
+        gpu.close()
+    assert np.array_equal(seen["shadow"], seen["upload"])
