@@ -24,7 +24,7 @@ from dataclasses import dataclass
 from .ir import P, S, T, Dag, ModelSourceError
 from .parse import ParsedModel
 
-CODEGEN_VERSION = "9"
+CODEGEN_VERSION = "10"
 
 
 @dataclass
@@ -43,6 +43,12 @@ class EmitOptions:
     #: (measured on B200 with the branch-free math: +5 % HH, +12 % glial, +3.5 % calibration; the
     #: cap only keeps very large user models from outgrowing the instruction cache)
     unroll_below: int = int(os.environ.get("KNPEMI_UNROLL_BELOW", "600"))
+    #: "fast" only: exponentials of affine functions of one state whose slopes are integer
+    #: multiples of a common base share one exp and a multiplication chain (codegen/fuse_exp.py;
+    #: HH: six exp -> one exp + 8 multiplications).  Costs up to ~max_exp_power * 1.5e-16 relative
+    #: accuracy on the rewritten rates, against the path's parity bar of 1e-10.
+    fuse_exp: bool = os.environ.get("KNPEMI_FUSE_EXP", "1") != "0"
+    max_exp_power: int = 96
 
 
 @dataclass
@@ -289,7 +295,8 @@ class _Emitter:
         w = L.append
         w(f"// GENERATED by knpemi_b200.codegen v{CODEGEN_VERSION} -- do not edit.")
         w(f"// model {name!r} from {pm.source_file}:{pm.lineno}")
-        w(f"// options: default_block={self.opts.default_block} math={self.opts.math}")
+        w(f"// options: default_block={self.opts.default_block} math={self.opts.math}"
+          f" fuse_exp={int(self.fast and self.opts.fuse_exp)}")
         w('#include <math.h>')
         w('#include "kem_math.cuh"')
         w('#include "kem_kernel.cuh"')
@@ -408,4 +415,11 @@ class _Emitter:
 
 
 def emit_model(pm: ParsedModel, name: str, ns: int, np_: int, opts: EmitOptions | None = None) -> EmittedModel:
-    return _Emitter(pm, ns, np_, opts or EmitOptions()).emit(name)
+    opts = opts or EmitOptions()
+    fused = []
+    if opts.math == "fast" and opts.fuse_exp:
+        from .fuse_exp import fuse_exponentials
+        pm, fused = fuse_exponentials(pm, opts.max_exp_power)
+    em = _Emitter(pm, ns, np_, opts).emit(name)
+    em.stats["fused_exp"] = fused
+    return em

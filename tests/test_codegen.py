@@ -1,4 +1,5 @@
 """RHS -> CUDA generator: parser, DAG, dependency classes, emission (CPU only)."""
+import math
 import os
 
 import numpy as np
@@ -212,3 +213,86 @@ def test_gotran_boilerplate_is_accepted():
     assert dy == [(1 - 0.25) * math.exp(60.0 / 10) - 0.25, -cur] and p_after[2] == cur
     em = generate_from_source(_src(body), "gotran", 2, 3)
     assert em.out_cols == [2] and em.used_cols == [0, 1]
+
+
+# ------------------------------------------------------------------ shared exponentials
+@pytest.mark.parametrize("name", MODEL_NAMES)
+def test_shared_exponential_rewrite_stays_within_its_error_bound(name):
+    """codegen/fuse_exp.py: the rewritten right-hand side, evaluated with Python floats, against
+    the DAG as written, on the golden RHS inputs plus random physiological ones: every rewritten
+    exponential within 2e-14 relative, and no amplified error in the derivatives."""
+    from knpemi_b200.codegen.fuse_exp import fuse_exponentials
+    ode = builtin(name)
+    pm = parse_model_source(open(ode.__file__).read(), filename=ode.__file__)
+    fused, report = fuse_exponentials(pm)
+    if name.startswith("glial"):
+        assert report == [] and fused is pm          # two exps of incommensurate slopes: untouched
+        return
+    # HH rates: exp((25-u)/10) - 1 stays as written, the two other /10 exponentials are shifts of
+    # it, exp(-u/18), exp(-u/20), exp(-u/80) are powers 40, 36, 9 of exp(-u/720)
+    assert [r["kind"] for r in report] == ["shift", "shift", "chain"]
+    assert report[2]["powers"] == [9, 36, 40] and sum(r["exps_replaced"] for r in report) == 5
+    g = np.load(os.path.join(GOLDEN, f"rhs_{name}.npz"))
+    rng = np.random.default_rng(11)
+    cases = [(g["t"][k], g["y"][k], g["p"][k]) for k in range(len(g["t"]))]
+    for k in range(200):
+        y = np.array(g["y"][k % len(g["t"])])
+        y *= 1.0 + 0.3 * rng.uniform(-1, 1, y.shape)
+        cases.append((g["t"][0], y, g["p"][k % len(g["t"])]))
+    from knpemi_b200.codegen.parse import ParsedModel
+    pairs = [pr for r in report for pr in r["nodes"]]
+    as_written = ParsedModel(pm.dag, {k: a for k, (a, _) in enumerate(pairs)}, {}, "", 0)
+    rewritten = ParsedModel(pm.dag, {k: b for k, (_, b) in enumerate(pairs)}, {}, "", 0)
+    worst_rate = worst_dy = 0.0
+    for t, y, p in cases:
+        a, pa = evaluate(pm, t, y, p)
+        b, pb = evaluate(fused, t, y, p)
+        a, b = np.array(a), np.array(b)
+        if not np.all(np.isfinite(a)):
+            continue
+        ea, _ = evaluate(as_written, t, y, p)
+        eb, _ = evaluate(rewritten, t, y, p)
+        worst_rate = max(worst_rate, float(np.max(np.abs(np.array(ea) - eb) / np.abs(ea))))
+        # the derivatives: differences of rate terms, and x/(exp(x) - 1) amplifies by 1/|x|
+        scale = np.maximum(np.abs(a), 1e-3 * np.max(np.abs(a)) + 1e-300)
+        worst_dy = max(worst_dy, float(np.max(np.abs(a - b) / scale)))
+        assert np.array_equal(np.array(pa), np.array(pb), equal_nan=True)       # currents: no exp
+    print(name, "worst rate error", worst_rate, "worst derivative error", worst_dy)
+    assert worst_rate < 2e-14, worst_rate
+    assert worst_dy < 1e-11, worst_dy
+
+
+def test_shared_exponential_groups_chain_and_limits():
+    from knpemi_b200.codegen.fuse_exp import _chain, _commensurate, fuse_exponentials
+    steps = _chain([9, 36, 40, 72])
+    have = {1}
+    for k, a, b in steps:
+        assert a in have and b in have and a + b == k
+        have.add(k)
+    assert {9, 36, 40, 72} <= have and len(steps) == 8
+    assert _commensurate([-100.0, -1000 / 18, -50.0, -12.5], 96)[1] == [72, 40, 36, 9]
+    assert _commensurate([1.0, -2.0], 96) is None                 # opposite signs
+    assert _commensurate([1.0, math.pi], 96) is None              # incommensurate
+    assert _commensurate([1.0, 97.0], 96) is None                 # power above the limit
+    # offsets that depend on parameters are hoisted, not left in the loop
+    src = _src(["a = math.exp((states[0] - parameters[0]) / 10.0)",
+                "b = math.exp((states[0] + 3.0) / 5.0)",
+                "c = math.exp(states[0] / 2.5)",
+                "values[0] = a * b * c"])
+    pm = parse_model_source(src)
+    fused, report = fuse_exponentials(pm)
+    assert report[0]["powers"] == [1, 2, 4] and report[0]["exps_replaced"] == 3
+    em = generate_from_source(src, "fuse_probe", 1, 1)
+    loop = em.source[em.source.index("void deriv"):em.source.index("void outputs")]
+    assert loop.count("kem::exp") == 1
+    hoist = em.source[em.source.index("void hoist"):em.source.index("void deriv")]
+    assert hoist.count("kem::exp") == 1
+    for y0 in (-3.0, 0.1, 7.5):
+        a, _ = evaluate(pm, 0.0, [y0], [1.25])
+        b, _ = evaluate(fused, 0.0, [y0], [1.25])
+        assert abs(a[0] - b[0]) <= 1e-14 * abs(a[0])
+    # off: every exp as written
+    em = generate_from_source(src, "fuse_probe", 1, 1, EmitOptions(fuse_exp=False))
+    assert em.source[em.source.index("void deriv"):em.source.index("void outputs")].count("kem::exp") == 3
+    em = generate_from_source(src, "fuse_probe", 1, 1, EmitOptions(math="libm"))
+    assert em.source[em.source.index("void deriv"):em.source.index("void outputs")].count("exp(") == 3
