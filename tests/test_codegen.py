@@ -296,3 +296,60 @@ def test_shared_exponential_groups_chain_and_limits():
     assert em.source[em.source.index("void deriv"):em.source.index("void outputs")].count("kem::exp") == 3
     em = generate_from_source(src, "fuse_probe", 1, 1, EmitOptions(math="libm"))
     assert em.source[em.source.index("void deriv"):em.source.index("void outputs")].count("exp(") == 3
+
+
+def test_shared_exponential_rewrite_on_random_rate_expressions():
+    """Random right-hand sides built from exponentials of affine functions of two states, with
+    rational slopes, constant and parameter-dependent offsets and every kind of consumer: each
+    rewritten exponential stays within the documented bound of the one as written, and
+    exponentials that feed a difference are never derived from a chain."""
+    from knpemi_b200.codegen.fuse_exp import fuse_exponentials
+    from knpemi_b200.codegen.parse import ParsedModel
+    rng = np.random.default_rng(2024)
+    n_fused = n_models = 0
+    for trial in range(int(os.environ.get("KNPEMI_FUSE_TRIALS", "60"))):
+        body, terms = [], []
+        base = [float(rng.choice([0.5, 1.0, 2.5, 12.5, 40.0])) for _ in range(2)]
+        for k in range(int(rng.integers(2, 8))):
+            s = int(rng.integers(0, 2))
+            num, den = int(rng.integers(1, 9)), int(rng.choice([1, 1, 2, 3, 4, 9]))
+            sign = "-" if rng.random() < 0.7 else ""
+            off = rng.choice(["", " + 1.5", " - 0.25", " + parameters[0]", " - parameters[1] / 3.0"])
+            form = rng.integers(0, 3)
+            arg = {0: f"({sign}states[{s}]{off}) * {num}.0 / {den * base[s]}",
+                   1: f"({sign}{num}.0 * states[{s}] / {den}.0{off}) / {base[s]}",
+                   2: f"{sign}states[{s}] / {den * base[s] / num}{off}"}[int(form)]
+            body.append(f"e{k} = math.exp({arg})")
+            use = rng.integers(0, 5)
+            terms.append({0: f"3.0 * e{k}", 1: f"(e{k} - 1.0)", 2: f"1.0 / (e{k} + 1.0)",
+                          3: f"states[{s}] / (1.0 - e{k})", 4: f"e{k} / (2.0 + states[{1 - s}])"}[int(use)])
+        body.append("values[0] = " + " + ".join(terms[::2]))
+        body.append("values[1] = " + (" * ".join(terms[1::2]) if terms[1::2] else "states[0]"))
+        pm = parse_model_source(_src(body))
+        fused, report = fuse_exponentials(pm)
+        n_models += 1
+        if not report:
+            continue
+        n_fused += 1
+        parents = {}
+        for nid in pm.dag.reachable(list(pm.dy.values())):
+            for c in pm.dag.nodes[nid].args:
+                parents.setdefault(c, []).append(pm.dag.nodes[nid].op)
+        for r in report:
+            if r["kind"] == "chain":
+                assert max(r["powers"]) <= 96
+                for a, _ in r["nodes"]:
+                    assert "sub" not in parents.get(a, []), "an exp feeding a difference was chained"
+        pairs = [pr for r in report for pr in r["nodes"]]
+        written = ParsedModel(pm.dag, {k: a for k, (a, _) in enumerate(pairs)}, {}, "", 0)
+        rewritten = ParsedModel(pm.dag, {k: b for k, (_, b) in enumerate(pairs)}, {}, "", 0)
+        for _ in range(20):
+            y, p = rng.uniform(-3.0, 3.0, 2), rng.uniform(-1.0, 1.0, 2)
+            ea, _ = evaluate(written, 0.0, y, p)
+            eb, _ = evaluate(rewritten, 0.0, y, p)
+            err = np.abs(np.array(ea) - eb) / np.abs(ea)
+            assert np.all(err < 2 * 96 * 1.2e-16), (trial, err.max(), body)
+            da, _ = evaluate(pm, 0.0, y, p)
+            db, _ = evaluate(fused, 0.0, y, p)
+            assert np.all(np.isfinite(db) == np.isfinite(da))
+    assert n_fused >= n_models // 2, (n_fused, n_models)
