@@ -187,6 +187,15 @@ int kem_device_download(int dev, void *host_dst, const void *dev_src, size_t byt
 /* ---- pinned host memory for callers that want zero-staging transfers ---------- */
 int kem_host_alloc(void **ptr_out, size_t bytes);
 int kem_host_free(void *ptr);
+/* Page-lock memory the caller owns -- the `u.x.array` the reference's setters read
+ * (odeSolver.py:142) and its getters write (odeSolver.py:159-164) -- so that
+ * kem_set_column / kem_get_column / kem_step_io copy it directly instead of through
+ * the staging buffers.  Registering twice and unregistering unknown memory are no-ops.
+ * The memory must be unregistered before it is freed. */
+int kem_host_register(void *ptr, size_t bytes);
+int kem_host_unregister(void *ptr);
+/* 1 if transfers from/to `ptr` take the direct (page-locked) path, 0 if they are staged. */
+int kem_host_is_pinned(const void *ptr, int *pinned_out);
 
 /* ---- measurement helpers ------------------------------------------------------ */
 /* Dependent-chain-free DFMA micro-benchmark: the measured FP64 pipe peak of

@@ -1637,6 +1637,39 @@ int kem_host_free(void *ptr)
     return KEM_OK;
 }
 
+// Page-lock memory the caller owns (the array behind a dolfinx Function): afterwards the
+// setters, getters and kem_step_io see it as pinned and DMA directly instead of staging.
+int kem_host_register(void *ptr, size_t bytes)
+{
+    ARG(ptr && bytes > 0, "null pointer or zero size");
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return KEM_OK;
+    }
+    CK(e);
+    return KEM_OK;
+}
+
+int kem_host_unregister(void *ptr)
+{
+    ARG(ptr, "null pointer");
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e == cudaErrorHostMemoryNotRegistered) {
+        cudaGetLastError();
+        return KEM_OK;
+    }
+    CK(e);
+    return KEM_OK;
+}
+
+int kem_host_is_pinned(const void *ptr, int *pinned_out)
+{
+    ARG(ptr && pinned_out, "null argument");
+    *pinned_out = is_pinned(ptr) ? 1 : 0;
+    return KEM_OK;
+}
+
 // ------------------------------------------------------------------- measurement
 int kem_fp64_peak(int dev, double *tflops_out, double *ms_out)
 {

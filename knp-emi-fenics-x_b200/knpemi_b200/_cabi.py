@@ -98,6 +98,9 @@ SIGNATURES = {
     "kem_device_download": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "kem_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "kem_host_free": (C.c_int, [C.c_void_p]),
+    "kem_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "kem_host_unregister": (C.c_int, [C.c_void_p]),
+    "kem_host_is_pinned": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "kem_fp64_peak": (C.c_int, [C.c_int, _DP, _DP]),
     "kem_hbm_copy_peak": (C.c_int, [C.c_int, _DP]),
 }
@@ -184,6 +187,13 @@ class PinnedArray:
 
     def free(self):
         self.array = None
+
+
+def host_is_pinned(a) -> bool:
+    """True if transfers from/to the ndarray `a` take the direct (page-locked) path."""
+    out = C.c_int(0)
+    check(lib().kem_host_is_pinned(C.c_void_p(a.ctypes.data), C.byref(out)), "kem_host_is_pinned")
+    return bool(out.value)
 
 
 def fp64_peak(dev: int = 0) -> tuple[float, float]:

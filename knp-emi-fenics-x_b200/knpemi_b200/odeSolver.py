@@ -208,6 +208,7 @@ class MembraneModel:
         self.time = 0
 
         self._mask_cache = {}          # id(locator) -> (locator, mask)
+        self._registered = []          # host arrays page-locked by register_host_array
         self._stim_mask_key = "unset"
         self.last_step_times = None
 
@@ -219,6 +220,9 @@ class MembraneModel:
         h, self._h = getattr(self, "_h", None), None
         if h:
             self._lib.kem_destroy(h)
+        for a in getattr(self, "_registered", []):
+            self._lib.kem_host_unregister(a.ctypes.data)
+        self._registered = []
 
     def __del__(self):
         try:
@@ -342,6 +346,21 @@ class MembraneModel:
         self.last_step_times = {"ms_kernel": times.ms_kernel, "ms_total": times.ms_total,
                                 "ms_h2d": times.ms_h2d, "ms_d2h": times.ms_d2h}
         return self.last_step_times
+
+    def register_host_array(self, u):
+        '''Page-lock the host array behind `u` (a Function or an ndarray), once.
+
+        The reference's callers hand the same `u.x.array` to the setters and getters every PDE
+        step (utils.py:227-233, run_2D.py:105-109).  Ordinary (pageable) memory has to be copied
+        through staging buffers; a registered array is read and written by the GPU's copy engine
+        directly, so the unmodified call sequence moves at link speed.  The array is kept alive
+        and unregistered by :meth:`close`.  Returns `u`.'''
+        a = u.x.array if hasattr(u, "x") else u
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.size > 0):
+            raise KemError("register_host_array needs a non-empty contiguous float64 ndarray")
+        check(self._lib.kem_host_register(a.ctypes.data, a.nbytes), "kem_host_register")
+        self._registered.append(a)
+        return u
 
     # ------------------------------------------- device-resident PDE vectors (SURVEY.md 8f: f1, f3)
     def register_trace_map(self, map_id, bulk_indices):
