@@ -1,5 +1,6 @@
 """Times the unmodified reference call sequence (7 setters, step_lsoda, 4 getters) with
-pageable NumPy arrays, i.e. what solve_odes (run_2D.py:80-111) does per PDE step."""
+pageable NumPy arrays, i.e. what solve_odes (run_2D.py:80-111) does per PDE step; with
+`--register` the same calls again after MembraneModel.register_host_array on every array."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "tests"), os.path.join(ROOT, "knp-emi-fenics-x_b200"), ROOT]
@@ -17,7 +18,13 @@ ins = {k: ArrayFunction(P[:, ode.parameter_indices(k)].copy()) for k in ("K_e", 
 phi = ArrayFunction(S[:, 3].copy())
 I = {k: ArrayFunction(n) for k in ("Na", "K", "Cl")}
 loc = lambda x: x[0] < 20e-6
-for it in range(5):
+register = "--register" in sys.argv
+for it in range(8 if register else 5):
+    if register and it == 4:
+        t0 = time.perf_counter()
+        for u in [*ins.values(), phi, *I.values()]:
+            m.register_host_array(u)
+        print(f"registered 11 arrays of {8 * n / 1e6:.0f} MB in {1e3 * (time.perf_counter() - t0):.1f} ms")
     t0 = time.perf_counter()
     for k, u in ins.items():
         m.set_parameter(k, u)
