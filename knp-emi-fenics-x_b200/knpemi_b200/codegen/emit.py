@@ -49,6 +49,9 @@ class EmitOptions:
     #: accuracy on the rewritten rates, against the path's parity bar of 1e-10.
     fuse_exp: bool = os.environ.get("KNPEMI_FUSE_EXP", "1") != "0"
     max_exp_power: int = 96
+    #: "fast" only, experimental (off): chains of affine operations on one node collapse into one
+    #: FMA of that node (codegen/affine.py); checked on the CPU, not yet measured on the device
+    collapse_affine: bool = os.environ.get("KNPEMI_COLLAPSE_AFFINE", "0") == "1"
 
 
 @dataclass
@@ -296,7 +299,8 @@ class _Emitter:
         w(f"// GENERATED by knpemi_b200.codegen v{CODEGEN_VERSION} -- do not edit.")
         w(f"// model {name!r} from {pm.source_file}:{pm.lineno}")
         w(f"// options: default_block={self.opts.default_block} math={self.opts.math}"
-          f" fuse_exp={int(self.fast and self.opts.fuse_exp)}")
+          f" fuse_exp={int(self.fast and self.opts.fuse_exp)}"
+          + (" collapse_affine=1" if self.fast and self.opts.collapse_affine else ""))
         w('#include <math.h>')
         w('#include "kem_math.cuh"')
         w('#include "kem_kernel.cuh"')
@@ -420,6 +424,11 @@ def emit_model(pm: ParsedModel, name: str, ns: int, np_: int, opts: EmitOptions 
     if opts.math == "fast" and opts.fuse_exp:
         from .fuse_exp import fuse_exponentials
         pm, fused = fuse_exponentials(pm, opts.max_exp_power)
+    collapsed = []
+    if opts.math == "fast" and opts.collapse_affine:
+        from .affine import collapse_affine
+        pm, collapsed = collapse_affine(pm)
     em = _Emitter(pm, ns, np_, opts).emit(name)
     em.stats["fused_exp"] = fused
+    em.stats["collapsed_affine"] = collapsed
     return em

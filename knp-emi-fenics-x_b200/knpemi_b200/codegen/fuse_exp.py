@@ -271,8 +271,16 @@ def fuse_exponentials(pm: ParsedModel, max_power: int = 96) -> tuple[ParsedModel
                            "nodes": [(nid, replace[nid]) for nid, _ in g]})
     if not replace:
         return pm, report
+    return substitute(pm, replace, shifted), report
 
-    # rebuild everything above the replaced nodes (nodes are immutable and hash-consed)
+
+def substitute(pm: ParsedModel, replace: dict, shifted: dict | None = None) -> ParsedModel:
+    """``pm`` with every node of ``replace`` exchanged for its image and everything above those
+    nodes rebuilt (nodes are immutable and hash-consed).  ``shifted`` maps a node of the form
+    value * factor to (value, factor): a constant or parameter-only scale of such a node joins
+    the factor instead of costing a second multiplication."""
+    dag = pm.dag
+    shifted = shifted or {}
     memo: dict[int, int] = {}
 
     def rebuild(root: int) -> int:
@@ -282,8 +290,13 @@ def fuse_exponentials(pm: ParsedModel, max_power: int = 96) -> tuple[ParsedModel
             if nid in memo:
                 stack.pop()
                 continue
-            if nid in replace:
-                memo[nid] = replace[nid]
+            if nid in replace and replace[nid] != nid:
+                # the image is rebuilt too: it may sit on top of other replaced nodes
+                image = replace[nid]
+                if image not in memo:
+                    stack.append(image)
+                    continue
+                memo[nid] = memo[image]
                 stack.pop()
                 continue
             node = dag.nodes[nid]
@@ -294,7 +307,7 @@ def fuse_exponentials(pm: ParsedModel, max_power: int = 96) -> tuple[ParsedModel
             args = tuple(memo[c] for c in node.args)
             folded = None
             if node.op == "mul":
-                # c * (x**k * exp(b))  ->  x**k * (c * exp(b)): the scale joins the shift factor
+                # c * (x**k * exp(b))  ->  x**k * (c * exp(b))
                 for x, c in ((args[0], args[1]), (args[1], args[0])):
                     if x in shifted and S not in dag.deps[c] and T not in dag.deps[c]:
                         folded = dag.binary("mul", shifted[x][0], dag.binary("mul", shifted[x][1], c))
@@ -316,4 +329,4 @@ def fuse_exponentials(pm: ParsedModel, max_power: int = 96) -> tuple[ParsedModel
 
     dy = {c: rebuild(n) for c, n in pm.dy.items()}
     out = {c: rebuild(n) for c, n in pm.out.items()}
-    return ParsedModel(dag=dag, dy=dy, out=out, source_file=pm.source_file, lineno=pm.lineno), report
+    return ParsedModel(dag=dag, dy=dy, out=out, source_file=pm.source_file, lineno=pm.lineno)

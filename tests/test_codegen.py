@@ -353,3 +353,48 @@ def test_shared_exponential_rewrite_on_random_rate_expressions():
             db, _ = evaluate(fused, 0.0, y, p)
             assert np.all(np.isfinite(db) == np.isfinite(da))
     assert n_fused >= n_models // 2, (n_fused, n_models)
+
+
+# ------------------------------------------------------------------ affine collapse (experimental)
+@pytest.mark.parametrize("name", MODEL_NAMES)
+def test_affine_collapse_keeps_the_right_hand_side(name):
+    """codegen/affine.py: chains of affine operations on one node become one FMA of that node.
+    Evaluated with Python floats (mul and add rounded separately, i.e. without the FMA's extra
+    accuracy) the rewritten right-hand side agrees with the one as written to rounding level."""
+    from knpemi_b200.codegen.affine import collapse_affine
+    from knpemi_b200.codegen.fuse_exp import fuse_exponentials
+    ode = builtin(name)
+    pm = parse_model_source(open(ode.__file__).read(), filename=ode.__file__)
+    g = np.load(os.path.join(GOLDEN, f"rhs_{name}.npz"))
+    rng = np.random.default_rng(5)
+    for start in (pm, fuse_exponentials(pm)[0]):
+        col, report = collapse_affine(start)
+        assert report, "every builtin model rescales its membrane potential"
+        assert all(r["operations_replaced"] >= 2 for r in report)
+        worst = 0.0
+        for k in range(150):
+            y = np.array(g["y"][k % len(g["t"])])
+            p = g["p"][k % len(g["t"])]
+            if k >= len(g["t"]):
+                y *= 1.0 + 0.2 * rng.uniform(-1, 1, y.shape)
+            a, pa = evaluate(start, g["t"][0], y, p)
+            b, pb = evaluate(col, g["t"][0], y, p)
+            a, b, pa, pb = np.array(a), np.array(b), np.array(pa), np.array(pb)
+            if not np.all(np.isfinite(a)):
+                continue
+            scale = np.maximum(np.abs(a), 1e-3 * np.max(np.abs(a)) + 1e-300)
+            worst = max(worst, float(np.max(np.abs(a - b) / scale)))
+            pscale = np.maximum(np.abs(pa), 1e-3 * np.max(np.abs(pa)) + 1e-300)
+            assert np.all(np.abs(pa - pb) / pscale < 1e-12)
+        assert worst < 1e-11, worst
+
+
+def test_affine_collapse_is_off_by_default_and_changes_the_source_when_on():
+    ode = builtin("hh_ideal")
+    off = codegen.generate(ode)
+    on = codegen.generate(ode, EmitOptions(collapse_affine=True))
+    assert off.stats["collapsed_affine"] == [] and "collapse_affine" not in off.source
+    assert on.stats["collapsed_affine"] and "collapse_affine=1" in on.source
+    assert on.source_hash != off.source_hash
+    loop = on.source[on.source.index("void deriv"):on.source.index("void outputs")]
+    assert "// u" not in loop            # the rescaled potential u = 1e3*(V + 65e-3) is gone
