@@ -524,7 +524,7 @@ def test_registered_host_arrays_take_the_direct_copy_path(built):
     """register_host_array page-locks the caller's `u.x.array` once; the unmodified setters and
     getters then copy it without staging and give the same values."""
     from knpemi_b200._cabi import host_is_pinned
-    n = 5003
+    n = 40003          # 320 kB per array: above malloc's mmap threshold, so no two arrays share a page
     gpu, cpu, X, rng = make_pair("hh_tissue", n)
     k_e, v, back = Func(3.0 + 0.01 * rng.normal(size=n)), Func(-70.0 + rng.normal(size=n)), Func(np.zeros(n))
     assert not host_is_pinned(k_e.x.array)
