@@ -49,6 +49,8 @@ class EmitOptions:
     #: accuracy on the rewritten rates, against the path's parity bar of 1e-10.
     fuse_exp: bool = os.environ.get("KNPEMI_FUSE_EXP", "1") != "0"
     max_exp_power: int = 96
+    #: also share exponentials whose offset depends on parameters (hoisted exp(offset); unbounded)
+    fuse_exp_param_offsets: bool = False
     #: "fast" only, experimental (off): chains of affine operations on one node collapse into one
     #: FMA of that node (codegen/affine.py); checked on the CPU, not yet measured on the device
     collapse_affine: bool = os.environ.get("KNPEMI_COLLAPSE_AFFINE", "0") == "1"
@@ -423,7 +425,7 @@ def emit_model(pm: ParsedModel, name: str, ns: int, np_: int, opts: EmitOptions 
     fused = []
     if opts.math == "fast" and opts.fuse_exp:
         from .fuse_exp import fuse_exponentials
-        pm, fused = fuse_exponentials(pm, opts.max_exp_power)
+        pm, fused = fuse_exponentials(pm, opts.max_exp_power, opts.fuse_exp_param_offsets)
     collapsed = []
     if opts.math == "fast" and opts.collapse_affine:
         from .affine import collapse_affine

@@ -35,8 +35,10 @@ alpha_n) the reference evaluates 0/0 = NaN and fails its ``assert success``; the
 Range: with the smallest slope as base and positive powers, every intermediate of a chain
 lies between 1 and the largest original exponential of the group, so a chain overflows or
 underflows only where an original ``exp(k*a*x)`` does; a constant shift is folded out only
-for |b| <= 40, a parameter-dependent one is the model's responsibility (a few units in
-every reference model).
+for |b| <= 40.  Exponentials whose offset depends on parameters (``exp((V - E_K)/k)``) are left
+alone unless ``param_offsets`` is set (``EmitOptions(fuse_exp_param_offsets=True)``): the
+hoisted factor ``exp(b)`` has no bound the generator could check, and none of the reference's
+models needs it.
 
 ``EmitOptions(fuse_exp=False)`` (or ``KNPEMI_FUSE_EXP=0``) and the "libm" build leave every
 ``exp`` as written.
@@ -165,7 +167,8 @@ def _chain(targets):
     return steps
 
 
-def fuse_exponentials(pm: ParsedModel, max_power: int = 96) -> tuple[ParsedModel, list]:
+def fuse_exponentials(pm: ParsedModel, max_power: int = 96,
+                      param_offsets: bool = False) -> tuple[ParsedModel, list]:
     """Rewrite ``pm`` so that exponentials of commensurate affine functions of one node share
     one ``exp``.  Returns the rewritten model and a report (one dict per fused group)."""
     dag = pm.dag
@@ -182,6 +185,8 @@ def fuse_exponentials(pm: ParsedModel, max_power: int = 96) -> tuple[ParsedModel
             continue
         if a.off is not None and dag.is_const(a.off) and abs(dag.fvalue(a.off)) > MAX_OFFSET:
             continue
+        if a.off is not None and not dag.is_const(a.off) and not param_offsets:
+            continue          # exp(b) of a parameter-dependent b has no bound known here
         by_atom.setdefault(a.atom, []).append((nid, a))
 
     # who reads each node: an exponential whose value is subtracted from something (the
