@@ -52,6 +52,11 @@ WORKLOADS = {
     "calibration_1e7": ("calibration", 10_000_000, "configs[3]: calibration ODE system, 10^7 DOFs"),
     "hh_tissue_1e7": ("hh_tissue", 10_000_000, "configs[4] neuron part: tissue HH, 10^7 DOFs per GPU"),
     "glial_tissue_1e7": ("glial_tissue", 10_000_000, "configs[4] glial part: mm_glial, 10^7 DOFs per GPU"),
+    # config #5: two membrane models (neurons tag 1, glia tag 2: run_stim_duration.py:171-181),
+    # 10^8 DOFs in total, strong-sharded over the GPUs of the run
+    "tissue_1e8": ([("hh_tissue", 50_000_000), ("glial_tissue", 50_000_000)],
+                   "configs[4]: EMIx-scale tissue membrane, HH (tag 1) + glial (tag 2), 10^8 DOFs in total, "
+                   "contiguous ranges of both models over the GPUs"),
 }
 
 # algorithmic HBM bytes per DOF-step: columns read + columns written, 8 B each
@@ -206,29 +211,66 @@ def host_threads() -> int:
         return max(os.cpu_count() or 1, 1)
 
 
-def run_cpu_oracle(model_name: str, target_seconds: float, seed: int):
-    """Oracle port of the reference stepping on the host cores: (DOF-steps/s, threads, sample)."""
+def l2_note(parts) -> str:
+    """Timing rule: inputs larger than the 126 MB L2, or say that they are not."""
+    mb = sum(ALGO_BYTES[name] * n for name, n in parts) / 1e6
+    if mb > 126:
+        return f"inputs {mb:.0f} MB per GPU > 126 MB L2, no flush needed"
+    return (f"inputs {mb:.0f} MB per GPU < 126 MB L2 and NOT flushed: informational workload, not a "
+            "contract line (compute-bound kernel)")
+
+
+def workload_parts(workload: str):
+    """[(model name, DOFs per GPU or in total)], description, strong?"""
+    spec = WORKLOADS[workload]
+    if isinstance(spec[0], (list, tuple)):
+        return list(spec[0]), spec[1], True
+    return [(spec[0], spec[1])], spec[2], False
+
+
+def cpu_port_rate(workload: str, steps: int, warmup: int, budget_s: float, seed: int = 20240611):
+    """The oracle port of the reference stepping (oracle/knpemi_oracle.c: the reference's
+    right-hand sides bit for bit, the row loop of odeSolver.py:107-122, scheme O1) on every
+    host thread, on a bounded sample of the workload split over its membrane models like the
+    workload itself.  One procedure for the reference arm and the in-arm `cpu_baseline`:
+    (DOF-steps/s, threads, sample text, seconds per step)."""
     from oracle import cpu_oracle
     from workloads import SETUP, synthetic_tables
     threads = host_threads()
-    cfg = SETUP[model_name]
-    c_probe = 4000 * max(threads, 1)
-    S, P, X, mask = synthetic_tables(model_name, c_probe, seed)
-    P[mask, _stim_col(model_name)] = cfg["stim"]
+    parts, _, _ = workload_parts(workload)
+    total = float(sum(n for _, n in parts))
+    probe = []
+    for name, n in parts:                       # cold probe: sizes the sample, not reported
+        c = max(int(4000 * threads * n / total), 1000)
+        S, P, X, mask = synthetic_tables(name, c, seed)
+        t0 = time.perf_counter()
+        cpu_oracle.step(name, S, P, 0.0, SETUP[name]["dt"], N_SUB, threads)
+        probe.append((c, time.perf_counter() - t0))
+    rate = sum(c for c, _ in probe) / max(sum(t for _, t in probe), 1e-9)
+    n_all = int(min(max(rate * budget_s / max(steps + warmup, 1), 4000 * threads), 4_000_000))
+    tabs = []
+    for name, n in parts:
+        k = max(int(n_all * n / total), 1000)
+        S, P, X, mask = synthetic_tables(name, k, seed)
+        P[mask, _stim_col(name)] = SETUP[name]["stim"]
+        tabs.append((name, k, S, P))
+    t = {name: 0.0 for name, _ in parts}
+
+    def one_step():
+        for name, k, S, P in tabs:
+            bad = cpu_oracle.step(name, S, P, t[name], SETUP[name]["dt"], N_SUB, threads)
+            assert bad == 0
+            t[name] += SETUP[name]["dt"]
+    for _ in range(warmup):
+        one_step()
     t0 = time.perf_counter()
-    cpu_oracle.step(model_name, S, P, 0.0, cfg["dt"], N_SUB, threads)
-    rate = c_probe / max(time.perf_counter() - t0, 1e-9)
-    n_steps = 4
-    n = int(min(max(rate * target_seconds / n_steps, c_probe), 4_000_000))
-    S, P, X, mask = synthetic_tables(model_name, n, seed)
-    P[mask, _stim_col(model_name)] = cfg["stim"]
-    t, t0 = 0.0, time.perf_counter()
-    for _ in range(n_steps):
-        bad = cpu_oracle.step(model_name, S, P, t, cfg["dt"], N_SUB, threads)
-        assert bad == 0
-        t += cfg["dt"]
+    for _ in range(steps):
+        one_step()
     el = time.perf_counter() - t0
-    return n * n_steps / el, threads, f"{n} DOFs x {n_steps} PDE steps of {model_name} (RK4 x {N_SUB}), {el:.1f} s"
+    n_used = sum(k for _, k, _, _ in tabs)
+    sample = (" + ".join(f"{k} DOFs of {name}" for name, k, _, _ in tabs)
+              + f" per step (RK4 x {N_SUB}), {steps} steps after {warmup} warm-up, {el:.1f} s")
+    return n_used * steps / el, threads, sample, el / steps
 
 
 def run_cpu_lsoda(model_name: str, n: int, seed: int):
@@ -268,39 +310,20 @@ def run_reference(args, dist: Dist):
     Each step is a bounded sample of the workload (rank 0 only)."""
     if dist.rank != 0:
         return
-    from oracle import cpu_oracle
-    from workloads import SETUP, synthetic_tables
-    model_name, n_per_gpu, cfg_text = WORKLOADS[args.workload]
-    cfg = SETUP[model_name]
-    threads = host_threads()
-    probe_n = 4000 * max(threads, 1)
-    S, P, X, mask = synthetic_tables(model_name, probe_n, 20240611)
-    t0 = time.perf_counter()
-    cpu_oracle.step(model_name, S, P, 0.0, cfg["dt"], N_SUB, threads)
-    rate = probe_n / max(time.perf_counter() - t0, 1e-9)
-    budget = 150.0 / max(args.steps + args.warmup, 1)            # whole run within ~2.5 min
-    n = int(min(max(rate * min(budget, 6.0), probe_n), 4_000_000))
-    S, P, X, mask = synthetic_tables(model_name, n, 20240611)
-    P[mask, _stim_col(model_name)] = cfg["stim"]
-    t = 0.0
-    for _ in range(args.warmup):
-        cpu_oracle.step(model_name, S, P, t, cfg["dt"], N_SUB, threads)
-        t += cfg["dt"]
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        bad = cpu_oracle.step(model_name, S, P, t, cfg["dt"], N_SUB, threads)
-        assert bad == 0
-        t += cfg["dt"]
-    el = time.perf_counter() - t0
-    value = n * args.steps / el
-    sample = f"{n} DOFs per step ({model_name}, RK4 x {N_SUB}) out of {n_per_gpu} per GPU"
+    from workloads import SETUP
+    parts, cfg_text, strong = workload_parts(args.workload)
+    value, threads, sample, s_per_step = cpu_port_rate(args.workload, args.steps, max(args.warmup, 1), 150.0)
+    head = parts[0][0]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": args.workload, "membrane_model": model_name, "baseline_config": cfg_text,
-                   "dofs_per_gpu": n_per_gpu, "scheme": "rk4", "n_sub": N_SUB, "dt": cfg["dt"]},
+        "config": {"workload": args.workload,
+                   "membrane_model": head if not strong else [name for name, _ in parts],
+                   "baseline_config": cfg_text,
+                   "dofs_per_gpu": parts[0][1] if not strong else None,
+                   "scheme": "rk4", "n_sub": N_SUB, "dt": SETUP[head]["dt"], "l2": l2_note(parts)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -311,17 +334,129 @@ def run_reference(args, dist: Dist):
 
 
 # ------------------------------------------------------------------------ GPU arm
+class Part:
+    """One MembraneModel of the workload (config #5 has two: neurons tag 1, glia tag 2)."""
+
+    def __init__(self, model_name, n, dev, seed, args, **model_kw):
+        from knpemi_b200.ducks import PointSpace
+        from knpemi_b200.odeSolver import MembraneModel
+        from workloads import SETUP, builtin, load_tables, synthetic_tables
+        self.name, self.n, self.cfg, self.ode = model_name, n, SETUP[model_name], builtin(model_name)
+        self.S, self.P, self.X, self.mask = synthetic_tables(model_name, n, seed=seed)
+        self.model = MembraneModel(self.ode, None, 1, PointSpace(self.X), devices=[dev], verbose=False,
+                                   n_sub=N_SUB, block=args.block, scheme=args.scheme, **model_kw)
+        load_tables(self.model, self.S, self.P)
+        self.stim = {"stim_amplitude": self.cfg["stim"]}
+        self.locator = lambda x: x[0] < 20e-6            # noqa: E731  (run_2D.py:264)
+        self.dt = self.cfg["dt"]
+        self.keep = []
+
+    def step_async(self):
+        self.model.step_async(self.dt, self.stim, self.locator)
+
+    # -- host buffers of one PDE<->ODE exchange (utils.py:217-233, run_2D.py:105-109)
+    def make_exchange_buffers(self, pinned=True):
+        from knpemi_b200 import _cabi
+        in_names, v_io, out_names = IO_COLUMNS[self.name]
+
+        def buf(src=None):
+            a = _cabi.pinned_empty(self.n) if pinned else np.empty(self.n)
+            a[:] = 0.0 if src is None else src
+            self.keep.append(a)
+            return a
+
+        self.ins = {("parameter", k): buf(self.P[:, self.ode.parameter_indices(k)]) for k in in_names}
+        self.outs = {("parameter", k): buf() for k in out_names}
+        self.v_io = v_io
+        if v_io:
+            self.ins[("state", "V")] = buf(np.asarray(self.model.states[:, self.ode.state_indices("V")]))
+            self.outs[("state", "V")] = buf()
+
+    def exchange(self):
+        tm = self.model.step_exchange(self.dt, self.ins, self.outs, self.stim, self.locator)
+        if self.v_io:                                 # the PDE side would hand phi_M back
+            self.ins[("state", "V")], self.outs[("state", "V")] = self.outs[("state", "V")], self.ins[("state", "V")]
+        return tm
+
+    def link_bytes(self):
+        """(bytes offered in, bytes that crossed host->device, bytes copied device->host, bytes the
+        host filled itself) per exchange, from where the library says the columns live."""
+        m = self.model
+        kept = [k for (what, k) in self.ins if what == "parameter" and m.column_location(what, k) in ("host", "discarded")]
+        literal = [k for (what, k) in self.outs if what == "parameter" and k in self.literal_outputs()]
+        return (8 * self.n * len(self.ins), 8 * self.n * (len(self.ins) - len(kept)),
+                8 * self.n * (len(self.outs) - len(literal)), 8 * self.n * len(literal), kept, literal)
+
+    def literal_outputs(self):
+        em = self.model._emitted
+        src = em.source
+        import re
+        m = re.search(r"const int CONST_OUT_COLS\[\] = \{([^}]*)\};", src)
+        n_const = int(re.search(r"USED_COLS, \d+, (\d+), CONST_OUT_COLS", src).group(1))
+        cols = [int(x) for x in m.group(1).split(",")][:n_const]
+        names = []
+        for (what, k) in self.outs:
+            if what == "parameter" and self.ode.parameter_indices(k) in cols:
+                names.append(k)
+        return names
+
+    def parity_sample(self, rows, steps=2):
+        """`rows` random DOFs of this part stepped by the CUDA path and by the CPU oracle from the
+        same tables: max relative error (the rule of tests/test_gpu_parity.py).  bench.py may call
+        the oracle only as a checker; this is that."""
+        from knpemi_b200.ducks import PointSpace
+        from knpemi_b200.odeSolver import MembraneModel
+        from oracle import cpu_oracle
+        from workloads import load_tables
+        rng = np.random.default_rng(5)
+        idx = np.sort(rng.choice(self.n, size=min(rows, self.n), replace=False))
+        S, P, X = self.S[idx].copy(), self.P[idx].copy(), self.X[idx]
+        mask = self.mask[idx]
+        m = MembraneModel(self.ode, None, 1, PointSpace(X), devices=self.model.devices, verbose=False, n_sub=N_SUB)
+        load_tables(m, S, P)
+        t = 0.0
+        for _ in range(steps):
+            m.step_lsoda(self.dt, self.stim, self.locator)
+            P[mask, self.ode.parameter_indices("stim_amplitude")] = self.cfg["stim"]
+            assert cpu_oracle.step(self.name, S, P, t, self.dt, N_SUB) == 0
+            t += self.dt
+        got_s = np.asarray(m.states)
+        out_cols = m.output_columns
+        got_c = np.asarray(m.parameters)[:, out_cols] if out_cols else np.zeros((len(idx), 0))
+        m.close()
+
+        def rel(a, b):
+            if b.size == 0:
+                return 0.0
+            scale = np.maximum(np.abs(b), 1e-6 * np.max(np.abs(b), axis=0, keepdims=True) + 1e-300)
+            return float(np.max(np.abs(a - b) / scale))
+        return {"rows": int(len(idx)), "pde_steps": steps, "max_rel_err_states": rel(got_s, S),
+                "max_rel_err_currents": rel(got_c, P[:, out_cols]), "tolerance": 1e-10,
+                "floor": "1e-6 x column max"}
+
+
+def measure_link(dev, dist):
+    """Host-link ceilings of this rank's GPU (pinned copies of 16 MB): alone, both directions,
+    and -- under torchrun -- with every rank of the box copying at the same time."""
+    from knpemi_b200 import _cabi
+    nbytes, reps = 16 << 20, 16
+    out = {"copy_bytes": nbytes}
+    if dist.rank == 0:
+        r = _cabi.link_ceiling(dev, nbytes, reps)
+        out["one_gpu_alone"] = {k: round(v, 2) for k, v in r.items() if isinstance(v, float)}
+    dist.barrier()
+    h, d = _cabi.link_probe(dev, nbytes, 3 * reps, 3 * reps)
+    hs, ds = dist.gather(h), dist.gather(d)
+    out["all_ranks_concurrent"] = {"h2d_per_rank": [round(v, 1) for v in hs], "d2h_per_rank": [round(v, 1) for v in ds],
+                                   "h2d_sum": round(sum(hs), 1), "d2h_sum": round(sum(ds), 1)}
+    return out
+
+
 def run_gpu(args, dist: Dist):
     from knpemi_b200 import _cabi
-    from knpemi_b200.ducks import PointSpace
-    from knpemi_b200.odeSolver import MembraneModel
-    from workloads import SETUP, builtin, load_tables, synthetic_tables
+    from knpemi_b200.ducks import ArrayFunction
 
-    model_name, n, cfg_text = WORKLOADS[args.workload]
-    if args.dofs:
-        n = int(args.dofs)
-    cfg = SETUP[model_name]
-    ode = builtin(model_name)
+    part_specs, cfg_text, strong = workload_parts(args.workload)
     dev = dist.local_rank
     if _cabi.device_count() <= dev:
         raise SystemExit("bench.py: no CUDA device for this rank -- the product has no CPU path")
@@ -331,133 +466,193 @@ def run_gpu(args, dist: Dist):
         from knpemi_b200.affinity import bind_to_device
         cpus = bind_to_device(dev)
 
-    S, P, X, mask = synthetic_tables(model_name, n, seed=20240611 + dist.rank)
-    model = MembraneModel(ode, None, 1, PointSpace(X), devices=[dev], verbose=False, n_sub=N_SUB,
-                          block=args.block, scheme=args.scheme)
-    load_tables(model, S, P)
-    stim = {"stim_amplitude": cfg["stim"]}
-    locator = lambda x: x[0] < 20e-6                 # noqa: E731  (run_2D.py:264)
-    dt = cfg["dt"]
+    if strong:
+        # config #5: fixed total size, contiguous DOF ranges of every membrane model over the ranks
+        parts = []
+        for k, (model_name, n_total) in enumerate(part_specs):
+            n_total = int(args.dofs) if args.dofs else n_total
+            per = (n_total + dist.world - 1) // dist.world
+            lo, hi = min(dist.rank * per, n_total), min((dist.rank + 1) * per, n_total)
+            parts.append(Part(model_name, hi - lo, dev, 20240611 + 97 * k + dist.rank, args,
+                              unread_inputs=args.unread_inputs))
+    else:
+        model_name, n = part_specs[0]
+        if args.dofs:
+            n = int(args.dofs)
+        parts = [Part(model_name, n, dev, 20240611 + dist.rank, args, unread_inputs=args.unread_inputs)]
+    head = max(parts, key=lambda p: p.n * (fp64_slots(p.name, N_SUB)[0] or 1.0))   # dominant kernel
+    n_rank = sum(p.n for p in parts)
 
     # ------------------------------------------------ resident: inputs already in HBM
+    def resident(steps):
+        for p in parts:
+            p.model.timer_begin()
+        for _ in range(steps):
+            for p in parts:
+                p.step_async()
+        return max(p.model.timer_end() for p in parts)
+
     for _ in range(max(args.warmup, 3)):
-        model.step_async(dt, stim, locator)
-    model.synchronize()
+        for p in parts:
+            p.step_async()
+    for p in parts:
+        p.model.synchronize()
     sampler = ClockSampler(dev)
     sampler.start()
     time.sleep(0.12)
     dist.barrier()
-    model.synchronize()
-    launches0 = model.launch_count()
+    launches0 = sum(p.model.launch_count() for p in parts)
     wall0 = time.perf_counter()
-    model.timer_begin()
-    for _ in range(args.steps):
-        model.step_async(dt, stim, locator)
-    ms = model.timer_end()
-    model.synchronize()
+    ms = resident(args.steps)
+    for p in parts:
+        p.model.synchronize()
     wall1 = time.perf_counter()
     dist.barrier()
-    launches = model.launch_count() - launches0
+    launches = sum(p.model.launch_count() for p in parts) - launches0
     clocks = sampler.stop(wall0, wall1)
-    dp45_steps = None
-    if args.scheme == "dp45":
-        model.step_stats()                                   # discard warm-up counts
-        for _ in range(3):
-            model.step_async(dt, stim, locator)
-        acc, rej = model.step_stats()
-        dp45_steps = {"accepted_per_dof_step": acc / (3.0 * n), "rejected_per_dof_step": rej / (3.0 * n),
-                      "rhs_evals_per_dof_step": 6.0 * (acc + rej) / (3.0 * n) + 1.0,
-                      "rtol": model.rtol, "atol": model.atol}
     ms_max = dist.max(ms)
-    total_dofs = dist.sum(float(n))
+    total_dofs = dist.sum(float(n_rank))
     value = total_dofs * args.steps / (ms_max * 1e-3)
     ms_per_step = ms_max / args.steps
 
+    # the same loop for at least a second: what the rate is once clocks and power have settled
+    sustained = None
+    if args.sustain_seconds > 0:
+        k_sus = max(int(args.sustain_seconds * 1e3 / max(ms / args.steps, 1e-3)) + 1, args.steps)
+        s2 = ClockSampler(dev)
+        s2.start()
+        time.sleep(0.06)
+        dist.barrier()
+        w0 = time.perf_counter()
+        ms_sus = resident(k_sus)
+        for p in parts:
+            p.model.synchronize()
+        w1 = time.perf_counter()
+        ms_sus = dist.max(ms_sus)
+        sustained = {"steps": k_sus, "seconds": ms_sus * 1e-3, "value": total_dofs * k_sus / (ms_sus * 1e-3),
+                     "unit": UNIT, "clocks": s2.stop(w0, w1)}
+
+    # kernel of the dominant part alone (roofline numerator's duration; equals ms/steps when
+    # the workload has one part)
+    if len(parts) > 1:
+        head.model.timer_begin()
+        for _ in range(args.steps):
+            head.step_async()
+        kernel_ms = head.model.timer_end() / args.steps
+    else:
+        kernel_ms = ms / args.steps
+
+    dp45_steps = None
+    if args.scheme == "dp45":
+        head.model.step_stats()                                   # discard warm-up counts
+        for _ in range(3):
+            head.step_async()
+        acc, rej = head.model.step_stats()
+        dp45_steps = {"accepted_per_dof_step": acc / (3.0 * head.n), "rejected_per_dof_step": rej / (3.0 * head.n),
+                      "rhs_evals_per_dof_step": 6.0 * (acc + rej) / (3.0 * head.n) + 1.0,
+                      "rtol": head.model.rtol, "atol": head.model.atol}
+
+    # ------------------------------------------------ host link ceiling (denominator of e2e)
+    link = measure_link(dev, dist) if not args.no_link_probe else None
+
     # ------------------------------------------------ end to end: host buffers through the API
-    in_names, v_io, out_names = IO_COLUMNS[model_name]
-    keep = []
-
-    def pinned(src=None):
-        pa = _cabi.PinnedArray(n)
-        keep.append(pa)
-        pa.array[:] = 0.0 if src is None else src
-        return pa.array
-
-    ins = {("parameter", k): pinned(P[:, ode.parameter_indices(k)]) for k in in_names}
-    outs = {("parameter", k): pinned() for k in out_names}
-    if v_io:
-        v_in, v_out = pinned(np.asarray(model.states[:, ode.state_indices("V")])), pinned()
-        ins[("state", "V")] = v_in
-        outs[("state", "V")] = v_out
-    h2d_offered = 8 * n * len(ins)
-    d2h = 8 * n * len(outs)
+    for p in parts:
+        p.make_exchange_buffers(pinned=True)
     e2e_steps = max(min(args.steps, 20), 3)
-    for _ in range(2):
-        model.step_exchange(dt, ins, outs, stim, locator)
+    for _ in range(3):
+        for p in parts:
+            p.exchange()
     dist.barrier()
     dev_ms = 0.0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        tm = model.step_exchange(dt, ins, outs, stim, locator)
-        dev_ms += tm["ms_total"]
-        if v_io:                                      # the PDE side would hand phi_M back
-            ins[("state", "V")], outs[("state", "V")] = outs[("state", "V")], ins[("state", "V")]
+        for p in parts:
+            dev_ms += p.exchange()["ms_total"]
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-    # bytes that really crossed the link: inputs to slots the right-hand side never reads
-    # (Cl_e, Cl_i for the HH models) are kept in a host shadow by the library
-    host_only = [k for (what, k) in ins if what == "parameter" and model.column_location(what, k) == "host"]
-    h2d = 8 * n * (len(ins) - len(host_only))
+    offered = h2d = d2h = filled = 0
+    kept_names, literal_names = [], []
+    for p in parts:
+        o, i, d, f, kept, lit = p.link_bytes()
+        offered, h2d, d2h, filled = offered + o, h2d + i, d2h + d, filled + f
+        kept_names += [f"{p.name}.{k}" for k in kept]
+        literal_names += [f"{p.name}.{k}" for k in lit]
     dist.barrier()
     e2e_ms_max = dist.max(e2e_wall_ms)
     e2e_per_rank = [round(v / e2e_steps, 3) for v in dist.gather(e2e_wall_ms)]
     e2e_dev_per_rank = [round(v / e2e_steps, 3) for v in dist.gather(dev_ms)]
     e2e_value = total_dofs * e2e_steps / (e2e_ms_max * 1e-3)
-    last = dict(model.last_step_times)
+    last = dict(head.model.last_step_times)
+    h2d_all, d2h_all = dist.sum(float(h2d)), dist.sum(float(d2h))
+    link_frac = None
+    if link:
+        # the exchange cannot finish before its larger direction has crossed the link at the
+        # rate measured with both directions busy on every rank
+        conc = link["all_ranks_concurrent"]
+        floor_ms = max(h2d_all / (conc["h2d_sum"] * 1e9), d2h_all / (conc["d2h_sum"] * 1e9)) * 1e3
+        link_frac = {"floor_ms_per_step": floor_ms, "measured_ms_per_step": e2e_ms_max / e2e_steps,
+                     "frac": floor_ms / (e2e_ms_max / e2e_steps),
+                     "h2d_gbs_achieved": h2d_all / (e2e_ms_max / e2e_steps * 1e-3) / 1e9,
+                     "d2h_gbs_achieved": d2h_all / (e2e_ms_max / e2e_steps * 1e-3) / 1e9,
+                     "definition": "floor = max over directions of bytes that crossed the link / the N-way "
+                                   "concurrent bidirectional pinned-copy rate measured in this run"}
 
     # ------------------------------------------------ the reference's own call sequence, unmodified:
-    # 7 setter calls + step_lsoda + 4 getter calls per PDE step on pageable NumPy arrays
-    # (utils.py:227-233, run_2D.py:98-109) -- what a user sees without touching solve_odes
-    from knpemi_b200.ducks import ArrayFunction
-    calls = None
-    if v_io and in_names:
-        u_in = {k: ArrayFunction(P[:, ode.parameter_indices(k)].copy()) for k in in_names}
-        u_phi = ArrayFunction(np.asarray(model.states[:, ode.state_indices("V")]))
-        u_out = {k: ArrayFunction(n) for k in out_names}
+    # 7 setter calls + step_lsoda + 4 getter calls per PDE step on ordinary NumPy arrays the
+    # caller keeps (utils.py:227-233, run_2D.py:98-109) -- what a user sees without touching
+    # solve_odes.  Arrays that come back every step are page-locked by the library on their
+    # second sighting; `exchange="deferred"` is the one-keyword opt-in that pipelines the copies.
+    dropin = {}
+    p0 = parts[0]
+    in_names, v_io, out_names = IO_COLUMNS[p0.name]
+    if v_io and in_names and len(parts) == 1 and not args.no_dropin:
+        from knpemi_b200.ducks import PointSpace
+        from knpemi_b200.odeSolver import MembraneModel
+        from workloads import load_tables
+        for mode in ("immediate", "deferred"):
+            m = MembraneModel(p0.ode, None, 1, PointSpace(p0.X), devices=[dev], verbose=False, n_sub=N_SUB,
+                              exchange=mode, unread_inputs=args.unread_inputs)
+            load_tables(m, p0.S, p0.P)
+            u_in = {k: ArrayFunction(p0.P[:, p0.ode.parameter_indices(k)].copy()) for k in in_names}
+            u_phi = ArrayFunction(p0.S[:, p0.ode.state_indices("V")].copy())
+            u_out = {k: ArrayFunction(p0.n) for k in out_names}
 
-        def one_pde_step():
-            for k, u in u_in.items():
-                model.set_parameter(k, u)
-            model.set_membrane_potential(u_phi)
-            model.step_lsoda(dt, stim, locator)
-            model.get_membrane_potential(u_phi)
-            for k, u in u_out.items():
-                model.get_parameter(k, u)
+            def one_pde_step():
+                for k, u in u_in.items():
+                    m.set_parameter(k, u)
+                m.set_membrane_potential(u_phi)
+                m.step_lsoda(p0.dt, p0.stim, p0.locator)
+                m.get_membrane_potential(u_phi)
+                for k, u in u_out.items():
+                    m.get_parameter(k, u)
 
-        one_pde_step()
-        dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            one_pde_step()
-        call_ms = dist.max((time.perf_counter() - t0) * 1e3) / 3
-        calls = {"value": total_dofs / (call_ms * 1e-3), "unit": UNIT, "ms_per_step_wall": call_ms,
-                 "api": "set_parameter x6 + set_membrane_potential + step_lsoda + get_membrane_potential "
-                        "+ get_parameter x3, pageable host arrays (staged through pinned buffers)"}
+            for _ in range(3):            # the second step registers the arrays, the third runs on them
+                one_pde_step()
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                one_pde_step()
+            call_ms = dist.max((time.perf_counter() - t0) * 1e3) / 5
+            m.close()
+            dropin[mode] = {"value": total_dofs / (call_ms * 1e-3), "unit": UNIT, "ms_per_step_wall": call_ms,
+                            "fraction_of_step_exchange": (e2e_ms_max / e2e_steps) / call_ms}
+        dropin["api"] = ("set_parameter x6 + set_membrane_potential + step_lsoda + get_membrane_potential + "
+                         "get_parameter x3 on ordinary NumPy arrays (page-locked by the library on their "
+                         "second sighting); 'immediate' = defaults, 'deferred' = MembraneModel(exchange='deferred')")
 
-    # ------------------------------------------------ roofline of the fused kernel
+    # ------------------------------------------------ roofline of the fused kernel (dominant part)
     peak_tf, _ = _cabi.fp64_peak(dev)
-    slots, slots_src = fp64_slots(model_name, N_SUB)
+    slots, slots_src = fp64_slots(head.name, N_SUB)
     if dp45_steps and slots:
         # O3 spends a data-dependent number of RHS evaluations: scale the per-RHS count of the
         # O1 kernel (same generated right-hand side) by the measured evaluations per DOF-step
         slots = slots / (4 * N_SUB + 1) * dp45_steps["rhs_evals_per_dof_step"]
         slots_src += " x measured RHS evaluations of scheme O3 (excludes controller arithmetic)"
-    kernel_ms = ms / args.steps                       # this rank's average launch duration
-    roofline = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak_tf,
+    roofline = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak_tf, "kernel": f"kem_step_kernel<{head.name}>",
                 "peak_source": "measured in this run: kem_fp64_peak (8 independent DFMA chains/thread, "
                                "2 flop per DFMA); MEASURED_PEAKS.json has no fp64 entry",
                 "kernel_ms": kernel_ms}
     if slots:
-        achieved = 2.0 * slots * n / (kernel_ms * 1e-3) / 1e12
+        achieved = 2.0 * slots * head.n / (kernel_ms * 1e-3) / 1e12
         roofline.update({"achieved": achieved, "frac": achieved / peak_tf,
                          "fp64_pipe_instructions_per_dof_step": slots, "instruction_count_source": slots_src,
                          "convention": "every FP64-pipe instruction (DFMA/DMUL/DADD) occupies one DFMA issue "
@@ -470,65 +665,82 @@ def run_gpu(args, dist: Dist):
             hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json (of measured)"
     except (OSError, KeyError, ValueError):
         hbm_peak, hbm_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    hbm_achieved = ALGO_BYTES[model_name] * n / (kernel_ms * 1e-3) / 1e9
+    hbm_achieved = ALGO_BYTES[head.name] * head.n / (kernel_ms * 1e-3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "fp64_slots.json")) as f:
-            e = json.load(f).get(model_name, {})
+            e = json.load(f).get(head.name, {})
         if e.get("ncu_dram_bytes_per_dof_step"):
-            traffic = e["ncu_dram_bytes_per_dof_step"] * n
+            traffic = e["ncu_dram_bytes_per_dof_step"] * head.n
     except (OSError, ValueError):
         pass
     roofline["traffic"] = traffic
     roofline["hbm"] = {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                        "frac": hbm_achieved / hbm_peak, "peak_source": hbm_src,
-                       "algorithmic_bytes_per_dof_step": ALGO_BYTES[model_name]}
+                       "algorithmic_bytes_per_dof_step": ALGO_BYTES[head.name]}
 
-    info = model.launch_info(args.block)
-    model.close()
+    info = head.model.launch_info(args.block)
+
+    # ------------------------------------------------ parity sample at full size (checker only)
+    parity = None
+    if args.parity_rows > 0 and args.scheme == "rk4":
+        per = [dict(p.parity_sample(args.parity_rows), membrane_model=p.name) for p in parts]
+        worst = max(max(q["max_rel_err_states"], q["max_rel_err_currents"]) for q in per)
+        worst = dist.max(worst)
+        parity = {"parts": per, "max_rel_err_all_ranks": worst, "ok": bool(worst < 1e-10)}
+    for p in parts:
+        p.model.close()
 
     # ------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     cpu = None
     if dist.rank == 0 and dist.world == 1 and not args.no_cpu_baseline:
-        v, threads, sample = run_cpu_oracle(model_name, args.cpu_seconds, 20240611)
+        v, threads, sample, _ = cpu_port_rate(args.workload, 4, 1, args.cpu_seconds)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                "scheme": f"O1: RK4 x {N_SUB}, the scheme the GPU runs (apples to apples)",
-               "reference_semantics_lsoda": run_cpu_lsoda(model_name, 1500, 20240611)}
+               "reference_semantics_lsoda": run_cpu_lsoda(head.name, 1500, 20240611)}
 
     if dist.rank == 0:
+        rhs_evals = 4 * N_SUB + 1 if args.scheme == "rk4" else dp45_steps["rhs_evals_per_dof_step"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": dist.world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "membrane_model": model_name, "baseline_config": cfg_text,
-                       "dofs_per_gpu": n, "scheme": args.scheme, "n_sub": N_SUB if args.scheme == "rk4" else None,
-                       "dt": dt, "dp45": dp45_steps,
-                       "rhs_evals_per_dof_step": 4 * N_SUB + 1 if args.scheme == "rk4"
-                       else dp45_steps["rhs_evals_per_dof_step"], "stimulus": "masked, x[0] < 20e-6 (~32 % of DOFs)",
-                       "l2": (f"inputs {ALGO_BYTES[model_name] * n / 1e6:.0f} MB per GPU > 126 MB L2, no flush needed"
-                              if ALGO_BYTES[model_name] * n > 126e6 else
-                              f"inputs {ALGO_BYTES[model_name] * n / 1e6:.0f} MB per GPU < 126 MB L2 and NOT "
-                              "flushed: informational workload, not a contract line (compute-bound kernel)"),
-                       "parallelism": f"{dist.world} x contiguous DOF ranges, no collective",
-                       "rank0_cpu_affinity": f"{len(cpus)} CPUs local to GPU {dev}" if cpus else "unchanged",
-                       "block": args.block or 128, "registers_per_thread": info["registers_per_thread"],
-                       "blocks_per_sm": info["blocks_per_sm"]},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d * dist.world),
-                    "d2h_bytes_per_step": int(d2h * dist.world), "steps": e2e_steps,
-                    "h2d_bytes_offered_per_step": int(h2d_offered * dist.world),
-                    "inputs_kept_in_host_shadow": host_only,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            # `config` has exactly the keys of the reference arm's line (same workload, same scheme);
+            # everything descriptive about this arm is under `details`
+            "config": {"workload": args.workload,
+                       "membrane_model": head.name if not strong else [p.name for p in parts],
+                       "baseline_config": cfg_text,
+                       "dofs_per_gpu": part_specs[0][1] if not strong else None,
+                       "scheme": args.scheme, "n_sub": N_SUB if args.scheme == "rk4" else None,
+                       "dt": head.dt, "l2": l2_note(part_specs)},
+            "details": {"dofs_this_run_per_gpu": [p.n for p in parts], "dofs_total": int(total_dofs),
+                        "dp45": dp45_steps, "rhs_evals_per_dof_step": rhs_evals,
+                        "stimulus": "masked, x[0] < 20e-6 (~32 % of DOFs)",
+                        "parallelism": f"{dist.world} x contiguous DOF ranges, no collective",
+                        "rank0_cpu_affinity": f"{len(cpus)} CPUs local to GPU {dev}" if cpus else "unchanged",
+                        "unread_inputs": args.unread_inputs,
+                        "block": args.block or 128, "registers_per_thread": info["registers_per_thread"],
+                        "blocks_per_sm": info["blocks_per_sm"]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
+                    "d2h_bytes_per_step": int(d2h_all), "steps": e2e_steps,
+                    "h2d_bytes_offered_per_step": int(dist.world * offered) if not strong else None,
+                    "host_filled_bytes_per_step": int(filled),
+                    "inputs_not_sent": kept_names, "outputs_filled_on_host": literal_names,
                     "ms_per_step_wall": e2e_ms_max / e2e_steps, "ms_per_step_device": dev_ms / e2e_steps,
                     "ms_per_step_wall_per_rank": e2e_per_rank, "ms_per_step_device_per_rank": e2e_dev_per_rank,
-                    "last_step_ms": last,
+                    "last_step_ms": last, "link": link_frac,
                     "api": "MembraneModel.step_exchange (kem_step_io): the 7 input columns of one PDE step "
-                           "from pinned host memory (those the right-hand side never reads stay in a host "
-                           "shadow), fused step, 4 output columns back, chunk-pipelined",
-                    "unmodified_reference_calls": calls},
+                           "from pinned host memory, fused step, 4 output columns back, chunk-pipelined; inputs "
+                           "the right-hand side never reads follow config.unread_inputs, outputs the generated "
+                           "code assigns a literal are filled on the host",
+                    "dropin": dropin or None},
+            "link_ceiling": link,
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "sustained": sustained,
             "roofline": roofline,
-            "rhs_evals_per_s": value * (4 * N_SUB + 1 if args.scheme == "rk4"
-                                        else dp45_steps["rhs_evals_per_dof_step"]),
+            "parity_sample": parity,
+            "rhs_evals_per_s": value * rhs_evals,
         }
         if cpu:
             line["cpu_baseline"] = cpu
@@ -548,6 +760,14 @@ def main():
                     help="rk4 = scheme O1 (the benchmark's normative scheme); dp45 = error-controlled O3")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-link-probe", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true")
+    ap.add_argument("--unread-inputs", choices=["auto", "shadow", "upload", "discard"], default="discard",
+                    help="policy for pushed PDE columns the right-hand side never reads (Cl_e, Cl_i)")
+    ap.add_argument("--sustain-seconds", type=float, default=1.0,
+                    help="after the K timed steps, repeat the resident loop for at least this long")
+    ap.add_argument("--parity-rows", type=int, default=100_000,
+                    help="random DOFs of the workload checked against the CPU oracle (0 = off)")
     args = ap.parse_args()
     # exactly one line on stdout: library chatter (e.g. NCCL's version banner) goes to stderr
     real_stdout = os.fdopen(os.dup(1), "w")

@@ -8,8 +8,9 @@
  * are caller-owned and may come from NumPy (`arr.ctypes.data`), DLPack or
  * kem_host_alloc().  Every function returns 0 on success, a negative KEM_E_*
  * code on argument / CUDA errors (text via kem_last_error()), and kem_step*
- * return KEM_NONFINITE (> 0) when an integrated state is not finite -- the
- * counterpart of the reference's `assert success` (odeSolver.py:121).
+ * return a positive code when the integration failed -- KEM_NONFINITE (a state is
+ * not finite) or KEM_STEP_FAILED (the error-controlled scheme could not reach
+ * t0+dt) -- the counterpart of the reference's `assert success` (odeSolver.py:121).
  *
  * There is no CPU fallback: without a CUDA device kem_create() fails.
  * Thread-safety: one host thread per handle.
@@ -25,7 +26,8 @@ extern "C" {
 #endif
 
 #define KEM_OK 0
-#define KEM_NONFINITE 1
+#define KEM_NONFINITE 1      /* a state became non-finite */
+#define KEM_STEP_FAILED 2    /* KEM_SCHEME_DP45: step-size control gave up before t0+dt */
 #define KEM_E_ARG (-1)
 #define KEM_E_CUDA (-2)
 #define KEM_E_MODEL (-3)
@@ -106,10 +108,29 @@ int kem_get_column(kem_handle h, int kind, int col, double *host_dst, int64_t n)
 int kem_column_is_uniform(kem_handle h, int kind, int col, int *is_uniform_out, double *value_out);
 
 /* where a column currently lives: 0 = one value for all DOFs, 1 = per-DOF column in HBM,
- * 2 = per-DOF host shadow.  A parameter slot the generated right-hand side neither reads nor
- * writes (for the HH models: Cl_e, Cl_i) is kept on the host by kem_set_column / kem_step_io --
- * it is uploaded only if a masked setter, a device gather/scatter or a stimulus needs it there. */
+ * 2 = per-DOF host shadow, 3 = discarded.  A parameter slot the generated right-hand side
+ * neither reads nor writes (for the HH models: Cl_e, Cl_i) need not cross the host link; what
+ * kem_set_column / kem_step_io do with a full-column write to such a slot is the policy below. */
 int kem_column_location(kem_handle h, int kind, int col, int *location_out);
+
+/* Policy for full-column writes to parameter slots the right-hand side never touches
+ * (the reference stores them like any other column, odeSolver.py:142, and never reads them):
+ *   KEM_UNREAD_SHADOW   keep the values in a host-side shadow copy (getters return them; they
+ *                       are uploaded if a masked setter / stimulus / device gather needs them)
+ *   KEM_UNREAD_UPLOAD   treat the slot like any other column (one more DMA per write)
+ *   KEM_UNREAD_DISCARD  neither copy nor upload: the value is dropped; reading the column
+ *                       afterwards fails with KEM_E_ARG until it is written again under another
+ *                       policy.  For callers that push the PDE state every step and never read
+ *                       these slots back (update_ode_variables, utils.py:227-228).
+ *   KEM_UNREAD_AUTO     (default) pageable sources are shadowed; pinned sources are uploaded by
+ *                       kem_set_column (the idle link beats a host copy) and, by kem_step_io,
+ *                       shadowed with up to two GPUs on the host and uploaded with more (there
+ *                       the host memory system is the bottleneck). */
+#define KEM_UNREAD_AUTO 0
+#define KEM_UNREAD_SHADOW 1
+#define KEM_UNREAD_UPLOAD 2
+#define KEM_UNREAD_DISCARD 3
+int kem_set_unread_policy(kem_handle h, int policy);
 
 /* ---- stimulus mask: `stimulus_mask` of step_lsoda (odeSolver.py:98-100) ------- */
 /* Upload the 0/1 mask used by the next kem_step calls; NULL = every DOF (the
@@ -120,7 +141,7 @@ int kem_set_stimulus_mask(kem_handle h, const uint8_t *host_mask_or_null, int64_
 /* Advance every DOF from t0 to t0+dt.  The n_stim (column, value) pairs are the
  * `stimulus` dict, written stickily into the parameter table under the current
  * stimulus mask (odeSolver.py:110-112).  status_flags != NULL: wait for the
- * kernel and report (bit 0: non-finite state); NULL: enqueue only, errors
+ * kernel and report (bit 0: non-finite state, bit 1: DP45 step control failed); NULL: enqueue only, errors
  * surface at the next synchronising call. */
 int kem_step(kem_handle h, double t0, double dt, int n_sub, int scheme,
              int n_stim, const int *stim_cols, const double *stim_vals, int *status_flags);
@@ -130,12 +151,24 @@ int kem_step_timed(kem_handle h, double t0, double dt, int n_sub, int scheme,
                    int *status_flags, kem_step_times *times_out);
 /* One coupled PDE/ODE exchange (utils.py:217-233 + step + run_2D.py:105-109):
  * copy n_in host columns in, step, copy n_out host columns out, pipelined in
- * DOF chunks over each device's streams.  Synchronous. */
+ * DOF chunks over each device's streams.  Synchronous, except when every host buffer is
+ * page-locked and both status_flags and times_out are NULL: then the call only enqueues
+ * (the buffers must stay untouched until kem_sync or a kem_get_column, which follows the
+ * kernel chunk by chunk).  Output slots the generated code assigns a literal (I_ch_Cl = 0.0,
+ * mm_hh.py:225) and uniform columns are filled on the host instead of copied back. */
 int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme,
                 int n_stim, const int *stim_cols, const double *stim_vals,
                 int n_in, const kem_io_column *in, int n_out, const kem_io_column *out,
                 int *status_flags, kem_step_times *times_out);
 int kem_sync(kem_handle h);
+/* Launch the KEM_SCHEME_RK4 kernel of kem_step as `n_chunks` DOF chunks (tapered tail, two
+ * compute streams) instead of one grid: a kem_get_column into page-locked memory that
+ * follows then copies chunk c while chunk c+1 still computes.  1 (default) = one launch. */
+int kem_set_step_chunks(kem_handle h, int n_chunks);
+/* The DOF chunks kem_step_io / a chunked kem_step cut a range of n DOFs into (offsets and
+ * lengths, at most `cap` written, the count always returned): `target` equal chunks whose tail
+ * is tapered by halving so that the pipeline drains through a small last chunk.  No device needed. */
+int kem_plan_chunks(int64_t n, int target, int64_t *off_out, int64_t *len_out, int cap, int *count_out);
 /* tolerances of KEM_SCHEME_DP45; defaults are the reference's rtol 1e-8, atol 1e-10
  * (odeSolver.py:120) */
 int kem_set_tolerances(kem_handle h, double rtol, double atol);
@@ -190,12 +223,15 @@ int kem_host_free(void *ptr);
 /* Page-lock memory the caller owns -- the `u.x.array` the reference's setters read
  * (odeSolver.py:142) and its getters write (odeSolver.py:159-164) -- so that
  * kem_set_column / kem_get_column / kem_step_io copy it directly instead of through
- * the staging buffers.  Registering twice and unregistering unknown memory are no-ops.
- * The memory must be unregistered before it is freed. */
+ * the staging buffers.  Registrations are reference-counted per base address over all handles
+ * of the process (registering twice needs two unregisters); a range that overlaps a registered
+ * one, or memory another owner page-locked, is refused with KEM_E_ARG; unregistering unknown
+ * memory is a no-op.  The memory must be unregistered before it is freed. */
 int kem_host_register(void *ptr, size_t bytes);
 int kem_host_unregister(void *ptr);
-/* 1 if transfers from/to `ptr` take the direct (page-locked) path, 0 if they are staged. */
-int kem_host_is_pinned(const void *ptr, int *pinned_out);
+/* 1 if transfers from/to the WHOLE range [ptr, ptr+bytes) take the direct (page-locked) path,
+ * 0 if they are staged (cudaHostRegister pins pages: the first byte alone proves nothing). */
+int kem_host_is_pinned(const void *ptr, size_t bytes, int *pinned_out);
 
 /* ---- measurement helpers ------------------------------------------------------ */
 /* Dependent-chain-free DFMA micro-benchmark: the measured FP64 pipe peak of
@@ -203,6 +239,14 @@ int kem_host_is_pinned(const void *ptr, int *pinned_out);
 int kem_fp64_peak(int dev, double *tflops_out, double *ms_out);
 /* Device-to-device copy bandwidth of device `dev` in GB/s (read + write bytes). */
 int kem_hbm_copy_peak(int dev, double *gbs_out);
+/* Host-link ceiling of device `dev`, the denominator of the end-to-end exchange
+ * (the 7-in / 4-out column traffic of utils.py:217-233 + run_2D.py:105-109):
+ * `reps_h2d` copies of `bytes` host->device and `reps_d2h` copies device->host run
+ * concurrently on two streams from pinned memory of the calling thread; each
+ * direction's elapsed milliseconds are returned (0 reps = that direction idle).
+ * Unequal rep counts measure the shorter direction entirely under the other's load. */
+int kem_link_probe(int dev, size_t bytes, int reps_h2d, int reps_d2h, double *ms_h2d_out,
+                   double *ms_d2h_out);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -22,20 +23,42 @@ public:
         return *pool;
     }
 
-    void copy(void *dst, const void *src, size_t bytes)
+    void copy(void *dst, const void *src, size_t bytes) { run_parts(dst, src, 0.0, bytes); }
+
+    // dst[0:n] = value, spread over the pool (the host-side stand-in for the device->host copy
+    // of an output column whose value is known without asking the device)
+    void fill(double *dst, double value, size_t n) { run_parts(dst, nullptr, value, n * sizeof(double)); }
+
+    int threads() const { return (int)workers_.size() + 1; }
+
+private:
+    static void do_part(char *dst, const char *src, double value, size_t bytes)
+    {
+        if (src) {
+            memcpy(dst, src, bytes);
+        } else if (value == 0.0 && !std::signbit(value)) {
+            memset(dst, 0, bytes);
+        } else {
+            double *d = (double *)dst;
+            for (size_t i = 0; i < bytes / sizeof(double); ++i) d[i] = value;
+        }
+    }
+
+    void run_parts(void *dst, const void *src, double value, size_t bytes)
     {
         const size_t min_part = 1u << 20;
         int parts = (int)std::min<size_t>(workers_.size() + 1, (bytes + min_part - 1) / min_part);
         if (parts <= 1) {
-            memcpy(dst, src, bytes);
+            do_part((char *)dst, (const char *)src, value, bytes);
             return;
         }
-        std::unique_lock<std::mutex> call_lock(call_mu_);      // one parallel copy at a time
+        std::unique_lock<std::mutex> call_lock(call_mu_);      // one parallel operation at a time
         const size_t per = ((bytes + parts - 1) / parts + 63) / 64 * 64;
         {
             std::lock_guard<std::mutex> lk(mu_);
             dst_ = (char *)dst;
             src_ = (const char *)src;
+            value_ = value;
             bytes_ = bytes;
             per_ = per;
             next_ = 1;
@@ -44,12 +67,11 @@ public:
             ++generation_;
         }
         cv_.notify_all();
-        memcpy(dst, src, std::min(per, bytes));                 // part 0 on the calling thread
+        do_part((char *)dst, (const char *)src, value, std::min(per, bytes));   // part 0 on the caller
         std::unique_lock<std::mutex> lk(mu_);
         done_cv_.wait(lk, [&] { return pending_ == 0; });
     }
 
-private:
     CopyPool()
     {
         unsigned hw = std::thread::hardware_concurrency();
@@ -71,7 +93,7 @@ private:
                 if (next_ >= parts_) seen = generation_;
             }
             const size_t off = (size_t)part * per_;
-            if (off < bytes_) memcpy(dst_ + off, src_ + off, std::min(per_, bytes_ - off));
+            if (off < bytes_) do_part(dst_ + off, src_ ? src_ + off : nullptr, value_, std::min(per_, bytes_ - off));
             {
                 std::lock_guard<std::mutex> lk(mu_);
                 if (--pending_ == 0) done_cv_.notify_one();
@@ -84,6 +106,7 @@ private:
     std::condition_variable cv_, done_cv_;
     char *dst_ = nullptr;
     const char *src_ = nullptr;
+    double value_ = 0.0;
     size_t bytes_ = 0, per_ = 0;
     int next_ = 0, parts_ = 0, pending_ = 0;
     unsigned long generation_ = 0;

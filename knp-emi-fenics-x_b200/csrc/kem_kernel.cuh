@@ -302,7 +302,8 @@ kem_step_dp45_kernel(const __grid_constant__ KemArgs<M> a)
         a.y[c][i] = y[c];
         finite = finite && isfinite(y[c]);
     }
-    if (!finite || failed) atomicOr(a.flags, 1);
+    if (!finite) atomicOr(a.flags, 1);
+    if (failed) atomicOr(a.flags, 2);      // step-size control gave up (step limit / h underflow)
 
     // ---- step statistics: one atomic pair per warp
     if (a.stats) {
@@ -435,11 +436,13 @@ static inline double kem_npmod_host(double a, double b)
     return r;
 }
 
-#define KEM_DEFINE_MODEL(M, NAME_STR, HASH_STR, OUT_COLS, USED_COLS, N_USED)                  \
+#define KEM_DEFINE_MODEL(M, NAME_STR, HASH_STR, OUT_COLS, USED_COLS, N_USED, N_CONST, CONST_COLS,  \
+                         CONST_VALS)                                                          \
     extern "C" __attribute__((visibility("default"))) const KemModelDesc *kem_model_descriptor(void) \
     {                                                                                         \
         static KemModelDesc d = {KEM_MODEL_ABI_VERSION, NAME_STR, HASH_STR, M::NS, M::NP,     \
                                  M::NOUT, OUT_COLS, N_USED, USED_COLS, M::NT,                 \
-                                 &M::tonly, &kem_launch<M>, 0, &kem_launch_info<M>};          \
+                                 &M::tonly, &kem_launch<M>, 0, &kem_launch_info<M>,           \
+                                 N_CONST, CONST_COLS, CONST_VALS};                            \
         return &d;                                                                            \
     }

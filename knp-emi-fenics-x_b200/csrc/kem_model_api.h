@@ -11,7 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define KEM_MODEL_ABI_VERSION 6
+#define KEM_MODEL_ABI_VERSION 7
 #define KEM_MAX_STIM 4
 
 extern "C" {
@@ -62,6 +62,11 @@ typedef struct KemModelDesc {
     // static launch facts, for reporting
     int regs_per_thread;            // filled lazily by launch_info
     cudaError_t (*launch_info)(int *regs, int *max_blocks_per_sm, int block);
+    // output slots whose right-hand side is a literal (I_ch_Cl = 0.0 in the HH models,
+    // mm_hh.py:225): the kernel still stores them, but nothing has to ask the device for them
+    int n_const_out;
+    const int *const_out_cols;      // [n_const_out] parameter columns, subset of out_cols
+    const double *const_out_vals;   // [n_const_out]
 } KemModelDesc;
 
 typedef const KemModelDesc *(*kem_model_descriptor_fn)(void);

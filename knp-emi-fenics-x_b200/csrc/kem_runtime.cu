@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <map>
 #include <condition_variable>
 #include <mutex>
 #include <string>
@@ -227,9 +228,10 @@ constexpr int SMALL_RING = 8;
 constexpr size_t SMALL_BYTES = 64 * 1024;
 constexpr int N_STAGE = 3;
 constexpr size_t STAGE_BYTES = 8u << 20;
-constexpr int IO_MAX_CHUNKS = 64;
+constexpr int IO_MAX_CHUNKS = 96;
 constexpr int KEM_MAX_MAPS = 16;
 constexpr int IO_TARGET_CHUNKS = 16;   // measured best of 8/16/32/64 at 1e7 DOFs (profiles/r1_bench.md)
+constexpr int64_t IO_MIN_CHUNK = 1 << 16;   // smallest tail chunk of the pipeline (0.5 MB per column)
 
 struct Shard {
     int dev = 0;
@@ -256,8 +258,12 @@ struct Shard {
     // pinned staging for pageable host columns
     void *h_stage[N_STAGE] = {};
     cudaEvent_t stage_ev[N_STAGE] = {};
-    // per-chunk events of kem_step_io
+    // per-chunk events of kem_step_io / a chunked kem_step
     std::vector<cudaEvent_t> io_in, io_k0, io_k1, io_out;
+    // DOF chunks of the last chunked step; `chunks_live` while nothing else has been enqueued
+    // since, so that a getter may follow the kernel chunk by chunk instead of waiting for all
+    std::vector<int64_t> ch_off, ch_len;
+    bool chunks_live = false;
     // scheme O3: per-DOF warm-start step size, device counters [accepted, rejected]
     double *d_hsug = nullptr;
     int *d_perm = nullptr;                   // activity-sorted thread -> DOF map
@@ -284,7 +290,11 @@ struct kem_handle_s {
     std::vector<char> p_dead;         // np: 1 = neither read nor written by the RHS
     std::vector<char> p_host;         // np: 1 = current value lives in p_shadow, not on the device
     std::vector<std::vector<double>> p_shadow;
-    bool shadow_pinned_io = true;     // kem_step_io: pinned inputs to dead slots go to the shadow too
+    std::vector<char> p_discarded;    // np: 1 = value dropped on request (KEM_UNREAD_DISCARD)
+    int unread_policy = KEM_UNREAD_AUTO;
+    bool shadow_pinned_io = true;     // KEM_UNREAD_AUTO: pinned inputs of kem_step_io to dead slots are shadowed
+    std::vector<char> out_const_valid;   // per constant output slot: 1 = the column holds the literal
+    int step_chunks = 1;              // kem_step: launch the range as this many chunks (getter overlap)
     bool uni_dirty = true;
     int block = 0;
     int64_t launches = 0;
@@ -305,15 +315,72 @@ int ensure_stage(Shard &s)
     return KEM_OK;
 }
 
-bool is_pinned(const void *p)
+// ---- page-locked host ranges -------------------------------------------------------
+// A host buffer takes the direct DMA path only if EVERY byte of it is page-locked.
+// cudaHostRegister pins whole pages, so a small array can start inside a page that a
+// registered neighbour pinned while its tail is pageable: the first byte alone proves
+// nothing.  Ranges this library pinned itself (kem_host_alloc, kem_host_register) are
+// kept in a process-wide, reference-counted table and answer by containment; memory
+// somebody else pinned (torch, the caller) is accepted when the driver reports one
+// allocation range that covers the whole buffer.
+struct HostRange {
+    size_t bytes = 0;
+    int refs = 0;
+    bool registered = false;   // cudaHostRegister by this library (unregister on last release)
+};
+std::map<uintptr_t, HostRange> g_host_ranges;     // keyed by base address
+std::map<uintptr_t, uintptr_t> g_host_aliases;    // registered sub-range -> base of the owning range
+std::mutex g_host_mu;
+
+bool in_own_range(const void *p, size_t bytes)
 {
-    cudaPointerAttributes at;
-    cudaError_t e = cudaPointerGetAttributes(&at, p);
-    if (e != cudaSuccess) {
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    const uintptr_t a = (uintptr_t)p;
+    auto it = g_host_ranges.upper_bound(a);
+    if (it == g_host_ranges.begin()) return false;
+    --it;
+    return a >= it->first && a + bytes <= it->first + it->second.bytes;
+}
+
+// driver API, resolved at run time so that the library loads on a box without libcuda
+typedef int (*cuPointerGetAttribute_fn)(void *data, int attribute, unsigned long long ptr);
+cuPointerGetAttribute_fn driver_pointer_attribute()
+{
+    static cuPointerGetAttribute_fn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            f = nullptr;
+        }
+        return (cuPointerGetAttribute_fn)f;
+    }();
+    return fn;
+}
+
+bool is_pinned(const void *p, size_t bytes)
+{
+    if (!p || bytes == 0) return false;
+    if (in_own_range(p, bytes)) return true;
+    const char *first = (const char *)p, *last = first + bytes - 1;
+    cudaPointerAttributes a0, a1;
+    if (cudaPointerGetAttributes(&a0, first) != cudaSuccess ||
+        cudaPointerGetAttributes(&a1, last) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
-    return at.type == cudaMemoryTypeHost;
+    if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost) return false;
+    // both ends are page-locked: they must belong to ONE allocation that spans the buffer
+    if (cuPointerGetAttribute_fn get = driver_pointer_attribute()) {
+        unsigned long long start = 0;
+        size_t size = 0;
+        const int RANGE_START_ADDR = 11, RANGE_SIZE = 12;   // CU_POINTER_ATTRIBUTE_RANGE_*
+        if (get(&start, RANGE_START_ADDR, (unsigned long long)(uintptr_t)first) == 0 &&
+            get(&size, RANGE_SIZE, (unsigned long long)(uintptr_t)first) == 0)
+            return (uintptr_t)first >= start && (uintptr_t)first + bytes <= start + size;
+    }
+    return false;   // cannot prove it: take the staged path (always correct)
 }
 
 // host -> device, enqueued on `st`; pageable sources go through the pinned
@@ -399,12 +466,17 @@ int small_upload(Shard &s, void *dst, const void *src, size_t bytes)
 // true if the parameter column's current value is not in a per-DOF device column
 bool not_on_device(kem_handle h, int col)
 {
-    return h->p_uniform[col] || h->p_host[col] || (!h->shards.empty() && !h->shards[0].pcol[col]);
+    return h->p_uniform[col] || h->p_host[col] || h->p_discarded[col] ||
+           (!h->shards.empty() && !h->shards[0].pcol[col]);
 }
 
 // make the parameter column a per-DOF device column holding its current value
 int ensure_pcol(kem_handle h, int col)
 {
+    if (h->p_discarded[col])
+        return fail(KEM_E_ARG, "parameter column " + std::to_string(col) +
+                                   " was discarded (unread-input policy KEM_UNREAD_DISCARD): its value "
+                                   "is not available; write it again under another policy");
     for (Shard &s : h->shards) {
         CK(cudaSetDevice(s.dev));
         if (!s.pcol[col] && s.n > 0)
@@ -491,17 +563,110 @@ void build_ttab(const KemModelDesc *m, double t0, double dt, int n_sub, std::vec
     m->tonly(t0 + dt, &tab[(size_t)(2 * n_sub + 1) * nt]);
 }
 
-// DOF chunks of one pipelined exchange (kem_step_io): enough chunks that the pipeline
-// fill/drain (one chunk of kernel + D2H) is a few percent of the exchange, chunks large
-// enough (>= 128k DOFs) that each launch still fills the GPU for several waves.
-int io_chunks(int64_t n, int64_t *chunk_out)
+// DOF chunks of one pipelined exchange (kem_step_io) or of a chunked kem_step.  The body of
+// the range is cut into `target` equal chunks (each launch still fills the GPU for several
+// waves, each column copy is several MB); the tail is tapered: whenever at most four chunks
+// of the current size remain the size is halved, down to IO_MIN_CHUNK, so that the pipeline
+// drains through a small last chunk (kernel + copy of 64k DOFs) instead of a sixteenth of
+// the range.  KNPEMI_IO_TAPER=0 restores equal chunks.
+void plan_chunks(int64_t n, int target, std::vector<int64_t> &off, std::vector<int64_t> &len)
 {
-    int target = IO_TARGET_CHUNKS;
-    if (const char *e = getenv("KNPEMI_IO_CHUNKS")) target = std::max(1, std::min(atoi(e), IO_MAX_CHUNKS));
-    int64_t chunk = std::max<int64_t>((n + target - 1) / target, 1 << 17);
+    off.clear();
+    len.clear();
+    if (n <= 0) return;
+    if (const char *e = getenv("KNPEMI_IO_CHUNKS")) target = atoi(e);
+    target = std::max(1, std::min(target, IO_MAX_CHUNKS / 2));
+    static const bool taper = !(getenv("KNPEMI_IO_TAPER") && atoi(getenv("KNPEMI_IO_TAPER")) == 0);
+    int64_t chunk = std::max<int64_t>((n + target - 1) / target, 2 * IO_MIN_CHUNK);
     chunk = (chunk + 1023) / 1024 * 1024;
-    *chunk_out = chunk;
-    return (int)((n + chunk - 1) / chunk);
+    int64_t at = 0;
+    while (at < n) {
+        const int64_t rem = n - at;
+        if (taper && target > 1 && rem <= 4 * chunk && chunk > IO_MIN_CHUNK &&
+            (int)off.size() + 8 < IO_MAX_CHUNKS) {
+            chunk = std::max<int64_t>(((chunk / 2) + 1023) / 1024 * 1024, IO_MIN_CHUNK);
+            continue;
+        }
+        const int64_t take = ((int)off.size() + 1 >= IO_MAX_CHUNKS) ? rem : std::min(chunk, rem);
+        off.push_back(at);
+        len.push_back(take);
+        at += take;
+    }
+}
+
+int ensure_chunk_events(Shard &s, size_t n_chunks)
+{
+    CK(cudaSetDevice(s.dev));
+    while (s.io_in.size() < n_chunks) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e)); s.io_in.push_back(e);
+        CK(cudaEventCreate(&e)); s.io_k0.push_back(e);
+        CK(cudaEventCreate(&e)); s.io_k1.push_back(e);
+        CK(cudaEventCreate(&e)); s.io_out.push_back(e);
+    }
+    return KEM_OK;
+}
+
+// something other than a chunked step is about to be enqueued: getters go back to stream order
+void drop_live_chunks(kem_handle h)
+{
+    for (Shard &s : h->shards) s.chunks_live = false;
+}
+
+int const_out_index(kem_handle h, int kind, int col)
+{
+    if (kind != KEM_PARAM) return -1;
+    for (int k = 0; k < h->m->n_const_out; ++k)
+        if (h->m->const_out_cols[k] == col) return k;
+    return -1;
+}
+
+// a caller wrote to parameter column `col`: it no longer provably holds the literal
+void touch_param(kem_handle h, int kind, int col)
+{
+    const int k = const_out_index(h, kind, col);
+    if (k >= 0) h->out_const_valid[k] = 0;
+}
+
+// every step stores the literals again
+void mark_outputs_stored(kem_handle h)
+{
+    std::fill(h->out_const_valid.begin(), h->out_const_valid.end(), 1);
+}
+
+bool holds_literal(kem_handle h, int kind, int col, double *v)
+{
+    const int k = const_out_index(h, kind, col);
+    if (k < 0 || !h->out_const_valid[k]) return false;
+    *v = h->m->const_out_vals[k];
+    return true;
+}
+
+// Where a full-column write to a slot the right-hand side never touches goes.
+enum UnreadDest { DEST_SHADOW, DEST_UPLOAD, DEST_DISCARD };
+UnreadDest unread_destination(kem_handle h, bool io_call, bool pinned_src)
+{
+    switch (h->unread_policy) {
+        case KEM_UNREAD_SHADOW: return DEST_SHADOW;
+        case KEM_UNREAD_UPLOAD: return DEST_UPLOAD;
+        case KEM_UNREAD_DISCARD: return DEST_DISCARD;
+        default: break;
+    }
+    // KEM_UNREAD_AUTO.  A plain setter runs alone: a pinned source goes over the idle link
+    // faster (one DMA) than the host can copy it (80 MB: 1.5 ms against 3 ms), a pageable one
+    // would need the same host copy into staging plus the DMA, so it is shadowed.  kem_step_io
+    // overlaps everything: see shadow_pinned_inputs().
+    if (!pinned_src) return DEST_SHADOW;
+    if (!io_call) return DEST_UPLOAD;
+    return h->shadow_pinned_io ? DEST_SHADOW : DEST_UPLOAD;
+}
+
+void discard_store(kem_handle h, int col)
+{
+    h->p_uniform[col] = 0;
+    h->p_host[col] = 0;
+    h->p_discarded[col] = 1;
+    std::vector<double>().swap(h->p_shadow[col]);
 }
 
 struct StepPlan {
@@ -623,7 +788,7 @@ int launch_range(kem_handle h, Shard &s, const StepPlan &pl, int64_t off, int64_
     std::vector<double *> o(std::max(m->n_out, 1));
     for (int c = 0; c < m->ns; ++c) y[c] = s.ycol[c] + off;
     for (int c = 0; c < m->np; ++c) {
-        if (h->p_uniform[c] || h->p_host[c]) {      // (a host-shadowed slot is never read by the kernel)
+        if (h->p_uniform[c] || h->p_host[c] || h->p_discarded[c]) {   // (shadowed / discarded slots are never read)
             p[c] = s.d_uni + c;
             pm[c] = 0;
         } else {
@@ -690,13 +855,18 @@ int read_flags(kem_handle h, int *status_flags)
         flags |= *s.h_flags;
     }
     *status_flags = flags;
-    if (flags & 1) {
+    if (flags & 3) {
         for (Shard &s : h->shards) {
             CK(cudaSetDevice(s.dev));
             CK(cudaMemsetAsync(s.d_flags, 0, sizeof(int), s.stream));
         }
-        g_err = "kem_step: a membrane state became non-finite";
-        return KEM_NONFINITE;
+        if (flags & 1) {
+            g_err = "kem_step: a membrane state became non-finite";
+            return KEM_NONFINITE;
+        }
+        g_err = "kem_step: the error-controlled integrator (KEM_SCHEME_DP45) could not reach t0+dt within "
+                "its step limit / minimum step size at the requested tolerances";
+        return KEM_STEP_FAILED;
     }
     return KEM_OK;
 }
@@ -746,7 +916,8 @@ int kem_model_load(const char *so_path, int *model_id_out)
         dlclose(dl);
         return fail(KEM_E_MODEL, std::string(so_path) + ": model ABI version mismatch (regenerate)");
     }
-    if (d->ns < 1 || d->np < 0 || d->n_out < 0 || d->n_out > 64 || !d->launch || !d->tonly) {
+    if (d->ns < 1 || d->np < 0 || d->n_out < 0 || d->n_out > 64 || !d->launch || !d->tonly ||
+        d->n_const_out < 0 || d->n_const_out > d->n_out) {
         dlclose(dl);
         return fail(KEM_E_MODEL, std::string(so_path) + ": malformed model descriptor");
     }
@@ -824,6 +995,8 @@ int kem_create(int model_id, int64_t n_dof, int n_dev, const int *dev_ids,
     h->uni.assign(param_defaults, param_defaults + m->np);
     h->p_uniform.assign(m->np, 1);
     h->p_host.assign(m->np, 0);
+    h->p_discarded.assign(m->np, 0);
+    h->out_const_valid.assign(std::max(m->n_const_out, 0), 0);
     h->p_shadow.resize(m->np);
     h->p_dead.assign(m->np, 1);
     for (int k = 0; k < m->n_used; ++k) h->p_dead[m->used_cols[k]] = 0;
@@ -973,10 +1146,14 @@ int kem_set_uniform(kem_handle h, int kind, int col, double v)
         h->uni[col] = v;
         h->p_uniform[col] = 1;
         h->p_host[col] = 0;
+        h->p_discarded[col] = 0;
+        std::vector<double>().swap(h->p_shadow[col]);
         h->uni_dirty = true;
         return KEM_OK;
     }
     if (kind == KEM_PARAM) h->uni[col] = v;
+    touch_param(h, kind, col);
+    drop_live_chunks(h);
     for (Shard &s : h->shards) {
         if (s.n == 0) continue;
         CK(cudaSetDevice(s.dev));
@@ -994,10 +1171,17 @@ int kem_set_column(kem_handle h, int kind, int col, const double *src, int64_t n
     if (rc) return rc;
     ARG(n == h->n, "length must equal the handle's n_dof");
     ARG(src || n == 0, "null source");
-    if (kind == KEM_PARAM && h->p_dead[col] && n > 0) {
-        shadow_store(h, col, src);
-        return KEM_OK;
+    if (n == 0) return KEM_OK;
+    const bool pinned = is_pinned(src, (size_t)n * sizeof(double));
+    touch_param(h, kind, col);
+    if (kind == KEM_PARAM && h->p_dead[col]) {
+        switch (unread_destination(h, false, pinned)) {
+            case DEST_SHADOW: shadow_store(h, col, src); return KEM_OK;
+            case DEST_DISCARD: discard_store(h, col); return KEM_OK;
+            case DEST_UPLOAD: break;
+        }
     }
+    drop_live_chunks(h);
     if (kind == KEM_PARAM && not_on_device(h, col)) {
         // becomes a per-DOF column; no need to pre-fill, every row is overwritten
         for (Shard &s : h->shards) {
@@ -1006,8 +1190,9 @@ int kem_set_column(kem_handle h, int kind, int col, const double *src, int64_t n
         }
         h->p_uniform[col] = 0;
         h->p_host[col] = 0;
+        h->p_discarded[col] = 0;
+        std::vector<double>().swap(h->p_shadow[col]);
     }
-    const bool pinned = n > 0 && is_pinned(src);
     for (Shard &s : h->shards) {
         rc = copy_in(s, col_ptr(s, kind, col), src + s.begin, (size_t)s.n * sizeof(double), s.stream,
                      pinned);
@@ -1045,6 +1230,8 @@ int kem_set_column_masked(kem_handle h, int kind, int col, const double *src,
     if (rc) return rc;
     ARG(n == h->n, "length must equal the handle's n_dof");
     ARG((src && host_mask) || n == 0, "null source or mask");
+    touch_param(h, kind, col);
+    drop_live_chunks(h);
     if (kind == KEM_PARAM && not_on_device(h, col)) {
         rc = ensure_pcol(h, col);
         if (rc) return rc;
@@ -1073,6 +1260,8 @@ int kem_set_value_masked(kem_handle h, int kind, int col, double v, const uint8_
     if (rc) return rc;
     ARG(n == h->n, "length must equal the handle's n_dof");
     ARG(host_mask || n == 0, "null mask");
+    touch_param(h, kind, col);
+    drop_live_chunks(h);
     if (kind == KEM_PARAM && not_on_device(h, col)) {
         rc = ensure_pcol(h, col);
         if (rc) return rc;
@@ -1098,24 +1287,46 @@ int kem_get_column(kem_handle h, int kind, int col, double *dst, int64_t n)
     if (rc) return rc;
     ARG(n == h->n, "length must equal the handle's n_dof");
     ARG(dst || n == 0, "null destination");
+    if (n == 0) return KEM_OK;
+    double lit = 0.0;
     if (kind == KEM_PARAM && h->p_uniform[col]) {
-        std::fill(dst, dst + n, h->uni[col]);
+        CopyPool::get().fill(dst, h->uni[col], (size_t)n);
+        return KEM_OK;
+    }
+    if (holds_literal(h, kind, col, &lit)) {      // e.g. I_ch_Cl = 0.0: known without asking the device
+        CopyPool::get().fill(dst, lit, (size_t)n);
         return KEM_OK;
     }
     if (kind == KEM_PARAM && h->p_host[col]) {
         CopyPool::get().copy(dst, h->p_shadow[col].data(), (size_t)n * sizeof(double));
         return KEM_OK;
     }
-    const bool pinned = n > 0 && is_pinned(dst);
+    if (kind == KEM_PARAM && h->p_discarded[col])
+        return fail(KEM_E_ARG, "kem_get_column: parameter column " + std::to_string(col) +
+                                   " was discarded (KEM_UNREAD_DISCARD); its value is not kept");
+    const bool pinned = is_pinned(dst, (size_t)n * sizeof(double));
     for (Shard &s : h->shards) {
+        if (s.n == 0) continue;
+        if (pinned && s.chunks_live) {
+            // the last thing enqueued is a chunked step: follow it chunk by chunk on the
+            // device->host stream instead of waiting for the whole range
+            CK(cudaSetDevice(s.dev));
+            for (size_t c = 0; c < s.ch_off.size(); ++c) {
+                CK(cudaStreamWaitEvent(s.s_out, s.io_k1[c], 0));
+                CK(cudaMemcpyAsync(dst + s.begin + s.ch_off[c], col_ptr(s, kind, col) + s.ch_off[c],
+                                   (size_t)s.ch_len[c] * sizeof(double), cudaMemcpyDeviceToHost, s.s_out));
+            }
+            continue;
+        }
         rc = copy_out(s, dst + s.begin, col_ptr(s, kind, col), (size_t)s.n * sizeof(double), s.stream,
                       pinned);
         if (rc) return rc;
     }
     if (pinned)
         for (Shard &s : h->shards) {
+            if (s.n == 0) continue;
             CK(cudaSetDevice(s.dev));
-            CK(cudaStreamSynchronize(s.stream));
+            CK(cudaStreamSynchronize(s.chunks_live ? s.s_out : s.stream));
         }
     return KEM_OK;
 }
@@ -1137,7 +1348,7 @@ int kem_column_location(kem_handle h, int kind, int col, int *location_out)
     if (rc) return rc;
     ARG(location_out, "null output");
     if (kind == KEM_STATE) *location_out = 1;
-    else *location_out = h->p_uniform[col] ? 0 : (h->p_host[col] ? 2 : 1);
+    else *location_out = h->p_uniform[col] ? 0 : (h->p_host[col] ? 2 : (h->p_discarded[col] ? 3 : 1));
     return KEM_OK;
 }
 
@@ -1161,6 +1372,25 @@ int kem_set_stimulus_mask(kem_handle h, const uint8_t *host_mask, int64_t n)
 }
 
 // -------------------------------------------------------------------------- step
+// Enqueue the step of shard `s` as the chunks of its plan, alternating over the two compute
+// streams (one chunk's tail wave overlaps the next one's head), each chunk after `after[c]`
+// if given.  Records io_k0/io_k1 per chunk; `stream` is made to wait for all of them.
+static int launch_chunked(kem_handle h, Shard &s, const StepPlan &pl, const cudaEvent_t *after)
+{
+    const size_t n_chunks = s.ch_off.size();
+    static const bool two = getenv("KNPEMI_IO_ONE_COMPUTE_STREAM") == nullptr;
+    CK(cudaSetDevice(s.dev));
+    for (size_t c = 0; c < n_chunks; ++c) {
+        cudaStream_t sk = (two && (c & 1)) ? s.stream2 : s.stream;
+        if (after) CK(cudaStreamWaitEvent(sk, after[c], 0));
+        CK(cudaEventRecord(s.io_k0[c], sk));
+        int rc = launch_range(h, s, pl, s.ch_off[c], s.ch_len[c], sk);
+        if (rc) return rc;
+        CK(cudaEventRecord(s.io_k1[c], sk));
+    }
+    return KEM_OK;
+}
+
 int kem_step_timed(kem_handle h, double t0, double dt, int n_sub, int scheme, int n_stim,
                    const int *stim_cols, const double *stim_vals, int *status_flags,
                    kem_step_times *times)
@@ -1169,15 +1399,33 @@ int kem_step_timed(kem_handle h, double t0, double dt, int n_sub, int scheme, in
     StepPlan pl;
     int rc = prepare_step(h, t0, dt, n_sub, scheme, n_stim, stim_cols, stim_vals, pl);
     if (rc) return rc;
+    drop_live_chunks(h);
+    // a chunked launch lets the getters that follow copy chunk c while chunk c+1 still runs
+    // (kem_set_step_chunks; scheme O3 sorts the whole range and stays one launch)
+    const bool chunked = h->step_chunks > 1 && scheme == KEM_SCHEME_RK4;
     for (Shard &s : h->shards) {
         if (times) {
             CK(cudaSetDevice(s.dev));
             CK(cudaEventRecord(s.ev_a, s.stream));
         }
-        rc = launch_range(h, s, pl, 0, s.n);
-        if (rc) return rc;
+        if (chunked && s.n >= 4 * IO_MIN_CHUNK) {
+            plan_chunks(s.n, h->step_chunks, s.ch_off, s.ch_len);
+            rc = ensure_chunk_events(s, s.ch_off.size());
+            if (rc) return rc;
+            CK(cudaEventRecord(s.ev_c, s.stream));          // stream2 must see the table uploads
+            CK(cudaStreamWaitEvent(s.stream2, s.ev_c, 0));
+            rc = launch_chunked(h, s, pl, nullptr);
+            if (rc) return rc;
+            const size_t nc = s.ch_off.size();
+            if (nc >= 2) CK(cudaStreamWaitEvent(s.stream, s.io_k1[(nc - 1) & 1 ? nc - 1 : nc - 2], 0));
+            s.chunks_live = true;
+        } else {
+            rc = launch_range(h, s, pl, 0, s.n);
+            if (rc) return rc;
+        }
         if (times) CK(cudaEventRecord(s.ev_b, s.stream));
     }
+    mark_outputs_stored(h);
     if (times) {
         memset(times, 0, sizeof *times);
         for (Shard &s : h->shards) {
@@ -1200,6 +1448,10 @@ int kem_step(kem_handle h, double t0, double dt, int n_sub, int scheme, int n_st
                           nullptr);
 }
 
+// One whole PDE -> ODE -> PDE exchange.  Order of effects, as in the reference: the input
+// columns are written first (the setters of utils.py:227-233), then the step applies the
+// sticky stimulus and integrates (odeSolver.py:108-122), then the outputs are read
+// (run_2D.py:105-109).  Everything is validated and classified before anything changes.
 int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n_stim,
                 const int *stim_cols, const double *stim_vals, int n_in, const kem_io_column *in,
                 int n_out, const kem_io_column *out, int *status_flags, kem_step_times *times)
@@ -1207,49 +1459,111 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
     NvtxRange nvtx_range("kem_step_io");
     ARG(h, "null handle");
     ARG(n_in >= 0 && n_out >= 0 && (in || !n_in) && (out || !n_out), "bad io arrays");
+    ARG(n_stim >= 0 && n_stim <= KEM_MAX_STIM && (n_stim == 0 || (stim_cols && stim_vals)),
+        "bad stimulus arrays");
     int rc;
+    const size_t col_bytes = (size_t)h->n * sizeof(double);
+    const bool masked = !h->shards.empty() && h->shards[0].has_mask;
+    // what the stimulus of this step does to a parameter column: 0 nothing, 1 rows under the
+    // mask, 2 every row (the column ends up uniform, whatever the inputs say)
+    auto stim_effect = [&](int kind, int col) {
+        if (kind != KEM_PARAM) return 0;
+        for (int k = 0; k < n_stim; ++k)
+            if (stim_cols[k] == col) return masked ? 1 : 2;
+        return 0;
+    };
+    auto stim_value = [&](int col) {
+        double v = 0.0;
+        for (int k = 0; k < n_stim; ++k)
+            if (stim_cols[k] == col) v = stim_vals[k];
+        return v;
+    };
+
+    // ---- 1. validate and classify; the handle is not modified in this phase
+    struct FillOut { double *host; double value; };
+    std::vector<kem_io_column> dev_in, dev_out, shadow_in, shadow_out, discard_in;
+    std::vector<FillOut> fill_out;
     bool all_pinned = true;
-    // columns that really cross the host link; inputs to slots the RHS never reads stay in
-    // their host shadow, outputs that live in a host shadow are copied from it
-    std::vector<kem_io_column> dev_in, dev_out, shadow_in, shadow_out;
     for (int k = 0; k < n_in; ++k) {
         rc = check_col(h, in[k].kind, in[k].col, __func__);
         if (rc) return rc;
         ARG(in[k].host || h->n == 0, "null input column");
-        if (in[k].kind == KEM_PARAM && h->p_dead[in[k].col] && h->n > 0 &&
-            (h->shadow_pinned_io || !is_pinned(in[k].host))) {
-            shadow_in.push_back(in[k]);
-            continue;
+        if (h->n == 0) continue;
+        const int eff = stim_effect(in[k].kind, in[k].col);
+        if (eff == 2) continue;                     // overwritten on every row by the stimulus
+        const bool pinned = is_pinned(in[k].host, col_bytes);
+        if (in[k].kind == KEM_PARAM && h->p_dead[in[k].col] && eff == 0) {
+            const UnreadDest d = unread_destination(h, true, pinned);
+            if (d == DEST_SHADOW) { shadow_in.push_back(in[k]); continue; }
+            if (d == DEST_DISCARD) { discard_in.push_back(in[k]); continue; }
         }
         dev_in.push_back(in[k]);
-        all_pinned = all_pinned && (h->n == 0 || is_pinned(in[k].host));
-        if (in[k].kind == KEM_PARAM && not_on_device(h, in[k].col)) {
-            for (Shard &s : h->shards) {
-                CK(cudaSetDevice(s.dev));
-                if (!s.pcol[in[k].col] && s.n > 0)
-                    CK(cudaMalloc(&s.pcol[in[k].col], (size_t)s.n * sizeof(double)));
-            }
-            h->p_uniform[in[k].col] = 0;
-            h->p_host[in[k].col] = 0;
-            std::vector<double>().swap(h->p_shadow[in[k].col]);
-        }
+        all_pinned = all_pinned && pinned;
     }
+    auto listed = [](const std::vector<kem_io_column> &v, int kind, int col) {
+        for (const kem_io_column &c : v)
+            if (c.kind == kind && c.col == col) return true;
+        return false;
+    };
     for (int k = 0; k < n_out; ++k) {
         rc = check_col(h, out[k].kind, out[k].col, __func__);
         if (rc) return rc;
         ARG(out[k].host || h->n == 0, "null output column");
-        ARG(!(out[k].kind == KEM_PARAM && h->p_uniform[out[k].col]),
-            "output column is uniform; read it with kem_get_column");
-        bool from_shadow = out[k].kind == KEM_PARAM && h->p_host[out[k].col];
-        for (const kem_io_column &c : shadow_in)
-            from_shadow = from_shadow || (out[k].kind == KEM_PARAM && c.col == out[k].col);
-        if (from_shadow) {
-            shadow_out.push_back(out[k]);
+        if (h->n == 0) continue;
+        const int kind = out[k].kind, col = out[k].col;
+        const int ci = const_out_index(h, kind, col);
+        if (ci >= 0) {                              // stored as a literal by every step
+            fill_out.push_back({out[k].host, h->m->const_out_vals[ci]});
             continue;
         }
+        const int eff = stim_effect(kind, col);
+        if (eff == 2) {                             // uniform after this step's stimulus
+            fill_out.push_back({out[k].host, stim_value(col)});
+            continue;
+        }
+        const bool as_input = listed(dev_in, kind, col);
+        if (kind == KEM_PARAM && listed(discard_in, kind, col))
+            return fail(KEM_E_ARG, "kem_step_io: an output column is discarded by this call's inputs "
+                                   "(KEM_UNREAD_DISCARD)");
+        if (kind == KEM_PARAM && listed(shadow_in, kind, col)) { shadow_out.push_back(out[k]); continue; }
+        if (kind == KEM_PARAM && !as_input && eff == 0) {
+            if (h->p_uniform[col]) { fill_out.push_back({out[k].host, h->uni[col]}); continue; }
+            if (h->p_host[col]) { shadow_out.push_back(out[k]); continue; }
+            if (h->p_discarded[col])
+                return fail(KEM_E_ARG, "kem_step_io: output column was discarded (KEM_UNREAD_DISCARD)");
+        }
         dev_out.push_back(out[k]);
-        all_pinned = all_pinned && (h->n == 0 || is_pinned(out[k].host));
+        all_pinned = all_pinned && is_pinned(out[k].host, col_bytes);
     }
+
+    // ---- 2. stimulus, time tables (may make a stimulus column uniform or per-DOF)
+    // A discarded slot that is a masked stimulus target AND an input of this call gets its
+    // default back first, so that prepare_step can materialise it; the input then overwrites it.
+    for (const kem_io_column &c : dev_in)
+        if (c.kind == KEM_PARAM && h->p_discarded[c.col] && stim_effect(c.kind, c.col) == 1) {
+            h->p_discarded[c.col] = 0;
+            h->p_uniform[c.col] = 1;
+            h->uni_dirty = true;
+        }
+    StepPlan pl;
+    rc = prepare_step(h, t0, dt, n_sub, scheme, n_stim, stim_cols, stim_vals, pl);
+    if (rc) return rc;
+    drop_live_chunks(h);
+
+    // ---- 3. residency of the input columns, just before their copies are enqueued
+    for (const kem_io_column &c : dev_in) {
+        touch_param(h, c.kind, c.col);
+        if (c.kind != KEM_PARAM || !not_on_device(h, c.col)) continue;
+        for (Shard &s : h->shards) {
+            CK(cudaSetDevice(s.dev));
+            if (!s.pcol[c.col] && s.n > 0) CK(cudaMalloc(&s.pcol[c.col], (size_t)s.n * sizeof(double)));
+        }
+        h->p_uniform[c.col] = 0;                    // every row is overwritten by the copy below
+        h->p_host[c.col] = 0;
+        h->p_discarded[c.col] = 0;
+        std::vector<double>().swap(h->p_shadow[c.col]);
+    }
+    for (const kem_io_column &c : discard_in) discard_store(h, c.col);
     in = dev_in.data();
     n_in = (int)dev_in.size();
     out = dev_out.data();
@@ -1258,11 +1572,9 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
     auto host_side = [&]() {
         for (const kem_io_column &c : shadow_in) shadow_store(h, c.col, c.host);
         for (const kem_io_column &c : shadow_out)
-            CopyPool::get().copy(c.host, h->p_shadow[c.col].data(), (size_t)h->n * sizeof(double));
+            CopyPool::get().copy(c.host, h->p_shadow[c.col].data(), col_bytes);
+        for (const FillOut &f : fill_out) CopyPool::get().fill(f.host, f.value, (size_t)h->n);
     };
-    StepPlan pl;
-    rc = prepare_step(h, t0, dt, n_sub, scheme, n_stim, stim_cols, stim_vals, pl);
-    if (rc) return rc;
 
     if (!all_pinned) {
         // pageable host buffers: staged column copies around one kernel launch
@@ -1279,6 +1591,7 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
             if (rc) return rc;
             CK(cudaEventRecord(s.ev_c, s.stream));
         }
+        mark_outputs_stored(h);
         host_side();
         for (Shard &s : h->shards) {
             for (int k = 0; k < n_out; ++k) {
@@ -1309,62 +1622,62 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
         return KEM_OK;
     }
 
-    // pinned host buffers: DOF-chunked pipeline, H2D (s_in) | kernel (stream) | D2H (s_out)
+    // pinned host buffers: DOF-chunked pipeline, H2D (s_in) | kernel (stream, stream2) | D2H (s_out)
     for (Shard &s : h->shards) {
         if (s.n == 0) continue;
         CK(cudaSetDevice(s.dev));
-        int64_t chunk = 0;
-        const int n_chunks = io_chunks(s.n, &chunk);
-        while ((int)s.io_in.size() < n_chunks) {
-            cudaEvent_t e;
-            CK(cudaEventCreate(&e)); s.io_in.push_back(e);
-            CK(cudaEventCreate(&e)); s.io_k0.push_back(e);
-            CK(cudaEventCreate(&e)); s.io_k1.push_back(e);
-            CK(cudaEventCreate(&e)); s.io_out.push_back(e);
-        }
+        plan_chunks(s.n, IO_TARGET_CHUNKS, s.ch_off, s.ch_len);
+        const size_t n_chunks = s.ch_off.size();
+        rc = ensure_chunk_events(s, n_chunks);
+        if (rc) return rc;
         // the copy streams must see the table/uniform uploads and earlier work on `stream`
         CK(cudaEventRecord(s.ev_a, s.stream));
         CK(cudaStreamWaitEvent(s.s_in, s.ev_a, 0));
         CK(cudaStreamWaitEvent(s.stream2, s.ev_a, 0));
+        CK(cudaStreamWaitEvent(s.s_out, s.ev_a, 0));
         CK(cudaEventRecord(s.ev_b, s.s_in));   // t = 0 of this shard's exchange
-        const bool two = getenv("KNPEMI_IO_ONE_COMPUTE_STREAM") == nullptr;
-        for (int c = 0; c < n_chunks; ++c) {
-            const int64_t off = (int64_t)c * chunk;
-            const int64_t len = std::min(chunk, s.n - off);
+        for (size_t c = 0; c < n_chunks; ++c) {
             for (int k = 0; k < n_in; ++k)
-                CK(cudaMemcpyAsync(col_ptr(s, in[k].kind, in[k].col) + off, in[k].host + s.begin + off,
-                                   (size_t)len * sizeof(double), cudaMemcpyHostToDevice, s.s_in));
+                CK(cudaMemcpyAsync(col_ptr(s, in[k].kind, in[k].col) + s.ch_off[c],
+                                   in[k].host + s.begin + s.ch_off[c],
+                                   (size_t)s.ch_len[c] * sizeof(double), cudaMemcpyHostToDevice, s.s_in));
             CK(cudaEventRecord(s.io_in[c], s.s_in));
-            cudaStream_t sk = (two && (c & 1)) ? s.stream2 : s.stream;
-            CK(cudaStreamWaitEvent(sk, s.io_in[c], 0));
-            CK(cudaEventRecord(s.io_k0[c], sk));
-            rc = launch_range(h, s, pl, off, len, sk);
-            if (rc) return rc;
-            CK(cudaEventRecord(s.io_k1[c], sk));
+        }
+        rc = launch_chunked(h, s, pl, s.io_in.data());
+        if (rc) return rc;
+        for (size_t c = 0; c < n_chunks; ++c) {
             CK(cudaStreamWaitEvent(s.s_out, s.io_k1[c], 0));
             for (int k = 0; k < n_out; ++k)
-                CK(cudaMemcpyAsync(out[k].host + s.begin + off, col_ptr(s, out[k].kind, out[k].col) + off,
-                                   (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, s.s_out));
+                CK(cudaMemcpyAsync(out[k].host + s.begin + s.ch_off[c],
+                                   col_ptr(s, out[k].kind, out[k].col) + s.ch_off[c],
+                                   (size_t)s.ch_len[c] * sizeof(double), cudaMemcpyDeviceToHost, s.s_out));
             CK(cudaEventRecord(s.io_out[c], s.s_out));
         }
-        // later work on `stream` (the next step) must not overtake the D2H copies
+        // later work on `stream` (the next step) must not overtake the kernels of stream2 or the
+        // D2H copies (io_out of the last chunk follows every kernel chunk)
         CK(cudaStreamWaitEvent(s.stream, s.io_out[n_chunks - 1], 0));
     }
+    mark_outputs_stored(h);
     host_side();
+    if (!status_flags && !times) {
+        // enqueue-only (like kem_step with NULL flags): the caller keeps the pinned buffers
+        // untouched until a synchronising call; a getter that follows copies chunk by chunk
+        for (Shard &s : h->shards) s.chunks_live = s.n > 0;
+        return KEM_OK;
+    }
     if (times) memset(times, 0, sizeof *times);
     for (Shard &s : h->shards) {
         if (s.n == 0) continue;
         CK(cudaSetDevice(s.dev));
         CK(cudaStreamSynchronize(s.s_out));
         if (times) {
-            int64_t chunk = 0;
-            const int n_chunks = io_chunks(s.n, &chunk);
+            const size_t n_chunks = s.ch_off.size();
             float tot = 0, kern = 0, h2d = 0, d2h = 0, f = 0;
             CK(cudaEventElapsedTime(&tot, s.ev_b, s.io_out[n_chunks - 1]));
             CK(cudaEventElapsedTime(&h2d, s.ev_b, s.io_in[n_chunks - 1]));
             // chunk kernels overlap across the two compute streams: report the span from the
             // first kernel's start to the last kernel's end, not the sum
-            for (int c = std::max(0, n_chunks - 2); c < n_chunks; ++c) {
+            for (size_t c = n_chunks >= 2 ? n_chunks - 2 : 0; c < n_chunks; ++c) {
                 CK(cudaEventElapsedTime(&f, s.io_k0[0], s.io_k1[c]));
                 kern = std::max(kern, f);
             }
@@ -1386,6 +1699,35 @@ int kem_sync(kem_handle h)
     if (rc) return rc;
     int flags = 0;
     return read_flags(h, &flags);
+}
+
+int kem_set_unread_policy(kem_handle h, int policy)
+{
+    ARG(h, "null handle");
+    ARG(policy >= KEM_UNREAD_AUTO && policy <= KEM_UNREAD_DISCARD, "unknown policy");
+    h->unread_policy = policy;
+    return KEM_OK;
+}
+
+int kem_plan_chunks(int64_t n, int target, int64_t *off_out, int64_t *len_out, int cap, int *count_out)
+{
+    ARG(count_out && n >= 0, "bad arguments");
+    std::vector<int64_t> off, len;
+    plan_chunks(n, target, off, len);
+    *count_out = (int)off.size();
+    for (int k = 0; k < std::min<int>(cap, (int)off.size()); ++k) {
+        if (off_out) off_out[k] = off[k];
+        if (len_out) len_out[k] = len[k];
+    }
+    return KEM_OK;
+}
+
+int kem_set_step_chunks(kem_handle h, int n_chunks)
+{
+    ARG(h, "null handle");
+    ARG(n_chunks >= 1 && n_chunks <= IO_MAX_CHUNKS / 2, "n_chunks out of range");
+    h->step_chunks = n_chunks;
+    return KEM_OK;
 }
 
 int kem_set_activity_sort(kem_handle h, int enabled)
@@ -1498,6 +1840,7 @@ static int device_xfer_check(kem_handle h, int shard, int kind, int col, const v
 
 int kem_device_gather(kem_handle h, int shard, int kind, int col, const double *dev_src, int map_id)
 {
+    if (h) { touch_param(h, kind, col); drop_live_chunks(h); }
     int rc = device_xfer_check(h, shard, kind, col, dev_src, map_id, __func__);
     if (rc) return rc;
     if (kind == KEM_PARAM && not_on_device(h, col)) {
@@ -1534,6 +1877,7 @@ int kem_device_scatter(kem_handle h, int shard, int kind, int col, double *dev_d
 int kem_device_gather_diff(kem_handle h, int shard, int kind, int col, const double *dev_a, int map_a,
                            const double *dev_b, int map_b)
 {
+    if (h) { touch_param(h, kind, col); drop_live_chunks(h); }
     int rc = device_xfer_check(h, shard, kind, col, dev_a, map_a, __func__);
     if (rc) return rc;
     rc = device_xfer_check(h, shard, kind, col, dev_b, map_b, __func__);
@@ -1554,6 +1898,7 @@ int kem_device_gather_diff(kem_handle h, int shard, int kind, int col, const dou
 
 int kem_device_copy_in(kem_handle h, int shard, int kind, int col, const double *dev_src)
 {
+    if (h) { touch_param(h, kind, col); drop_live_chunks(h); }
     int rc = check_col(h, kind, col, __func__);
     if (rc) return rc;
     ARG(shard >= 0 && shard < (int)h->shards.size(), "shard out of range");
@@ -1627,34 +1972,92 @@ int kem_host_alloc(void **ptr_out, size_t bytes)
 {
     ARG(ptr_out, "null output");
     *ptr_out = nullptr;
-    CK(cudaHostAlloc(ptr_out, std::max<size_t>(bytes, 8), cudaHostAllocPortable));
+    bytes = std::max<size_t>(bytes, 8);
+    CK(cudaHostAlloc(ptr_out, bytes, cudaHostAllocPortable));
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    HostRange &r = g_host_ranges[(uintptr_t)*ptr_out];
+    r.bytes = bytes;
+    r.refs = 1;
+    r.registered = false;
     return KEM_OK;
 }
 
 int kem_host_free(void *ptr)
 {
-    if (ptr) CK(cudaFreeHost(ptr));
+    if (!ptr) return KEM_OK;
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        g_host_ranges.erase((uintptr_t)ptr);
+    }
+    CK(cudaFreeHost(ptr));
     return KEM_OK;
 }
 
 // Page-lock memory the caller owns (the array behind a dolfinx Function): afterwards the
 // setters, getters and kem_step_io see it as pinned and DMA directly instead of staging.
+// Registrations are reference-counted per base address across all handles of the process:
+// two models that register the same array share one cudaHostRegister, and the memory is
+// unpinned when the last of them releases it.
 int kem_host_register(void *ptr, size_t bytes)
 {
     ARG(ptr && bytes > 0, "null pointer or zero size");
-    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
-    if (e == cudaErrorHostMemoryAlreadyRegistered) {
-        cudaGetLastError();
+    const uintptr_t a = (uintptr_t)ptr;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    auto it = g_host_ranges.find(a);
+    if (it != g_host_ranges.end()) {
+        ARG(bytes <= it->second.bytes, "range is registered with a smaller size; unregister it first");
+        it->second.refs++;
         return KEM_OK;
     }
+    // a different base inside / across a range of ours: the caller would end up with a
+    // partially pinned buffer; say so instead of pretending
+    auto up = g_host_ranges.upper_bound(a);
+    if (up != g_host_ranges.end() && up->first < a + bytes)
+        return fail(KEM_E_ARG, "kem_host_register: range overlaps a registered range");
+    if (up != g_host_ranges.begin()) {
+        auto prev = std::prev(up);
+        if (prev->first + prev->second.bytes > a) {
+            if (a + bytes <= prev->first + prev->second.bytes) {   // a view into a pinned range
+                if (!prev->second.registered) return KEM_OK;       // kem_host_alloc memory: nothing to count
+                if (g_host_aliases.count(a))
+                    return fail(KEM_E_ARG, "kem_host_register: sub-range is already registered");
+                prev->second.refs++;
+                g_host_aliases[a] = prev->first;                   // unregister(ptr) finds the owner
+                return KEM_OK;
+            }
+            return fail(KEM_E_ARG, "kem_host_register: range overlaps a registered range");
+        }
+    }
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        // pinned by somebody else (not through this library): usable only if that pinning
+        // covers the whole buffer, which is_pinned() checks on every transfer
+        cudaGetLastError();
+        return fail(KEM_E_ARG, "kem_host_register: memory is (partly) page-locked by another owner");
+    }
     CK(e);
+    HostRange &r = g_host_ranges[a];
+    r.bytes = bytes;
+    r.refs = 1;
+    r.registered = true;
     return KEM_OK;
 }
 
 int kem_host_unregister(void *ptr)
 {
     ARG(ptr, "null pointer");
-    cudaError_t e = cudaHostUnregister(ptr);
+    uintptr_t a = (uintptr_t)ptr;
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    auto al = g_host_aliases.find(a);
+    if (al != g_host_aliases.end()) {
+        a = al->second;
+        g_host_aliases.erase(al);
+    }
+    auto it = g_host_ranges.find(a);
+    if (it == g_host_ranges.end() || !it->second.registered) return KEM_OK;   // unknown memory: no-op
+    if (--it->second.refs > 0) return KEM_OK;
+    g_host_ranges.erase(it);
+    cudaError_t e = cudaHostUnregister((void *)a);
     if (e == cudaErrorHostMemoryNotRegistered) {
         cudaGetLastError();
         return KEM_OK;
@@ -1663,10 +2066,10 @@ int kem_host_unregister(void *ptr)
     return KEM_OK;
 }
 
-int kem_host_is_pinned(const void *ptr, int *pinned_out)
+int kem_host_is_pinned(const void *ptr, size_t bytes, int *pinned_out)
 {
     ARG(ptr && pinned_out, "null argument");
-    *pinned_out = is_pinned(ptr) ? 1 : 0;
+    *pinned_out = is_pinned(ptr, std::max<size_t>(bytes, 1)) ? 1 : 0;
     return KEM_OK;
 }
 
@@ -1705,6 +2108,62 @@ int kem_fp64_peak(int dev, double *tflops_out, double *ms_out)
     CK(cudaEventDestroy(e1));
     CK(cudaStreamDestroy(st));
     CK(cudaFree(d_out));
+    return KEM_OK;
+}
+
+// Host-link ceiling of device `dev`: `reps_h2d` copies of `bytes` host->device on one stream
+// and `reps_d2h` copies device->host on another, enqueued interleaved (start skew ~10 us), pinned
+// host memory allocated by the calling thread (so its NUMA placement is the bench's).
+// A direction's elapsed time is first copy start -> its last copy end.  With unequal rep
+// counts the shorter direction is measured entirely under the other one's traffic.
+int kem_link_probe(int dev, size_t bytes, int reps_h2d, int reps_d2h, double *ms_h2d_out,
+                   double *ms_d2h_out)
+{
+    ARG(bytes >= 8 && reps_h2d >= 0 && reps_d2h >= 0 && reps_h2d + reps_d2h > 0, "bad probe size");
+    ARG(ms_h2d_out && ms_d2h_out, "null output");
+    CK(cudaSetDevice(dev));
+    void *h_a = nullptr, *h_b = nullptr, *d_a = nullptr, *d_b = nullptr;
+    CK(cudaHostAlloc(&h_a, bytes, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&h_b, bytes, cudaHostAllocDefault));
+    memset(h_a, 1, bytes);
+    memset(h_b, 2, bytes);
+    CK(cudaMalloc(&d_a, bytes));
+    CK(cudaMalloc(&d_b, bytes));
+    CK(cudaMemset(d_b, 0, bytes));
+    cudaStream_t s_in, s_out;
+    CK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    cudaEvent_t i0, i1, o0, o1;
+    CK(cudaEventCreate(&i0));
+    CK(cudaEventCreate(&i1));
+    CK(cudaEventCreate(&o0));
+    CK(cudaEventCreate(&o1));
+    // warm-up in both directions (first touch of the mappings)
+    CK(cudaMemcpyAsync(d_a, h_a, bytes, cudaMemcpyHostToDevice, s_in));
+    CK(cudaMemcpyAsync(h_b, d_b, bytes, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaStreamSynchronize(s_in));
+    CK(cudaStreamSynchronize(s_out));
+    CK(cudaEventRecord(i0, s_in));
+    CK(cudaEventRecord(o0, s_out));
+    for (int k = 0; k < std::max(reps_h2d, reps_d2h); ++k) {      // interleaved enqueue
+        if (k < reps_h2d) CK(cudaMemcpyAsync(d_a, h_a, bytes, cudaMemcpyHostToDevice, s_in));
+        if (k < reps_d2h) CK(cudaMemcpyAsync(h_b, d_b, bytes, cudaMemcpyDeviceToHost, s_out));
+    }
+    CK(cudaEventRecord(i1, s_in));
+    CK(cudaEventRecord(o1, s_out));
+    CK(cudaEventSynchronize(i1));
+    CK(cudaEventSynchronize(o1));
+    float a = 0.f, b = 0.f;
+    CK(cudaEventElapsedTime(&a, i0, i1));
+    CK(cudaEventElapsedTime(&b, o0, o1));
+    *ms_h2d_out = reps_h2d ? (double)a : 0.0;
+    *ms_d2h_out = reps_d2h ? (double)b : 0.0;
+    for (cudaEvent_t e : {i0, i1, o0, o1}) CK(cudaEventDestroy(e));
+    for (cudaStream_t s : {s_in, s_out}) CK(cudaStreamDestroy(s));
+    CK(cudaFree(d_a));
+    CK(cudaFree(d_b));
+    CK(cudaFreeHost(h_a));
+    CK(cudaFreeHost(h_b));
     return KEM_OK;
 }
 

@@ -17,7 +17,9 @@ KEM_STATE, KEM_PARAM = 0, 1
 KEM_SCHEME_RK4 = 0
 KEM_SCHEME_DP45 = 1
 KEM_NONFINITE = 1
+KEM_STEP_FAILED = 2
 KEM_MAX_STIM = 4
+UNREAD_POLICIES = {"auto": 0, "shadow": 1, "upload": 2, "discard": 3}
 
 
 class KemError(RuntimeError):
@@ -29,6 +31,12 @@ class NonFiniteStateError(AssertionError):
 
     Subclass of AssertionError: the reference signals integration failure with
     ``assert success`` (src/knpemi/odeSolver.py:121)."""
+
+
+class StepControlError(AssertionError):
+    """Scheme "dp45" could not reach t+dt within its step limit / minimum step size.
+
+    Subclass of AssertionError for the same reason as :class:`NonFiniteStateError`."""
 
 
 class kem_model_info(C.Structure):
@@ -78,6 +86,9 @@ SIGNATURES = {
                               C.c_int, C.POINTER(kem_io_column), C.c_int, C.POINTER(kem_io_column),
                               _IP, C.POINTER(kem_step_times)]),
     "kem_sync": (C.c_int, [_H]),
+    "kem_set_unread_policy": (C.c_int, [_H, C.c_int]),
+    "kem_set_step_chunks": (C.c_int, [_H, C.c_int]),
+    "kem_plan_chunks": (C.c_int, [C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int, _IP]),
     "kem_set_tolerances": (C.c_int, [_H, C.c_double, C.c_double]),
     "kem_set_activity_sort": (C.c_int, [_H, C.c_int]),
     "kem_get_step_stats": (C.c_int, [_H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -100,9 +111,10 @@ SIGNATURES = {
     "kem_host_free": (C.c_int, [C.c_void_p]),
     "kem_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "kem_host_unregister": (C.c_int, [C.c_void_p]),
-    "kem_host_is_pinned": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "kem_host_is_pinned": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "kem_fp64_peak": (C.c_int, [C.c_int, _DP, _DP]),
     "kem_hbm_copy_peak": (C.c_int, [C.c_int, _DP]),
+    "kem_link_probe": (C.c_int, [C.c_int, C.c_size_t, C.c_int, C.c_int, _DP, _DP]),
 }
 
 _lib = None
@@ -134,6 +146,8 @@ def check(rc: int, what: str = "") -> int:
     msg = lib().kem_last_error().decode(errors="replace")
     if rc == KEM_NONFINITE:
         raise NonFiniteStateError(msg or "non-finite membrane state")
+    if rc == KEM_STEP_FAILED:
+        raise StepControlError(msg or "error-controlled step failed")
     raise KemError(f"{what or 'libknpemi_b200'} failed (code {rc}): {msg}")
 
 
@@ -192,7 +206,7 @@ class PinnedArray:
 def host_is_pinned(a) -> bool:
     """True if transfers from/to the ndarray `a` take the direct (page-locked) path."""
     out = C.c_int(0)
-    check(lib().kem_host_is_pinned(C.c_void_p(a.ctypes.data), C.byref(out)), "kem_host_is_pinned")
+    check(lib().kem_host_is_pinned(C.c_void_p(a.ctypes.data), a.nbytes, C.byref(out)), "kem_host_is_pinned")
     return bool(out.value)
 
 
@@ -206,6 +220,26 @@ def hbm_copy_peak(dev: int = 0) -> float:
     g = C.c_double()
     check(lib().kem_hbm_copy_peak(dev, C.byref(g)), "kem_hbm_copy_peak")
     return g.value
+
+
+def link_probe(dev: int, nbytes: int, reps_h2d: int, reps_d2h: int) -> tuple[float, float]:
+    """(GB/s host->device, GB/s device->host) of `reps_*` concurrent pinned copies of `nbytes`."""
+    a, b = C.c_double(), C.c_double()
+    check(lib().kem_link_probe(dev, nbytes, reps_h2d, reps_d2h, C.byref(a), C.byref(b)), "kem_link_probe")
+    return (nbytes * reps_h2d / (a.value * 1e-3) / 1e9 if reps_h2d else 0.0,
+            nbytes * reps_d2h / (b.value * 1e-3) / 1e9 if reps_d2h else 0.0)
+
+
+def link_ceiling(dev: int = 0, nbytes: int = 64 << 20, reps: int = 12) -> dict:
+    """Measured pinned-copy ceilings of one GPU's host link, GB/s per direction: each direction
+    alone, both saturated, and each direction while the other one runs for twice as long."""
+    h_alone, _ = link_probe(dev, nbytes, reps, 0)
+    _, d_alone = link_probe(dev, nbytes, 0, reps)
+    h_both, d_both = link_probe(dev, nbytes, reps, reps)
+    h_loaded, _ = link_probe(dev, nbytes, reps, 2 * reps)
+    _, d_loaded = link_probe(dev, nbytes, 2 * reps, reps)
+    return {"h2d_alone": h_alone, "d2h_alone": d_alone, "h2d_both": h_both, "d2h_both": d_both,
+            "h2d_under_d2h": h_loaded, "d2h_under_h2d": d_loaded, "copy_bytes": nbytes, "reps": reps}
 
 
 class DeviceArray:

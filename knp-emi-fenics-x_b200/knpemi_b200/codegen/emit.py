@@ -24,7 +24,7 @@ from dataclasses import dataclass
 from .ir import P, S, T, Dag, ModelSourceError
 from .parse import ParsedModel
 
-CODEGEN_VERSION = "10"
+CODEGEN_VERSION = "11"
 
 
 @dataclass
@@ -168,11 +168,17 @@ class _Emitter:
         if op == "mul":
             return f"{a[0]} * {a[1]}"
         if op == "div":
-            if self.fast and ctx != "time":
-                num, den = n.args
+            num, den = n.args
+            if self.dag.is_const(den) and self.dag.fvalue(den) == 0.0:
+                raise ModelSourceError("division by the literal 0 in the model's right-hand side")
+            # The branch-free kem::rcp / kem::div trade the IEEE special cases (zero, infinite,
+            # denormal divisors give NaN) for speed inside the sub-step loop.  The parameter-only
+            # section runs once per DOF per PDE step: there the plain IEEE division costs nothing
+            # measurable and x/0 stays +-inf, c/(1+inf) stays 0 like in the reference's cfunc.
+            if self.fast and ctx == "dyn":
                 if self.dag.is_const(den):
                     return f"{a[0]} * {self.dev_lit(1.0 / self.dag.fvalue(den))}"
-                if ctx == "dyn" and den in self.rcp_hoist:
+                if den in self.rcp_hoist:
                     return f"{a[0]} * q.r{den}"
                 if self.dag.is_const(num):
                     if self.dag.fvalue(num) == 1.0:
@@ -299,7 +305,8 @@ class _Emitter:
         L = []
         w = L.append
         w(f"// GENERATED by knpemi_b200.codegen v{CODEGEN_VERSION} -- do not edit.")
-        w(f"// model {name!r} from {pm.source_file}:{pm.lineno}")
+        shown = "".join(ch if (ch.isalnum() or ch in "._-/") else "?" for ch in str(pm.source_file))
+        w(f"// model {name!r} from {shown}:{pm.lineno}")
         w(f"// options: default_block={self.opts.default_block} math={self.opts.math}"
           f" fuse_exp={int(self.fast and self.opts.fuse_exp)}"
           + (" collapse_affine=1" if self.fast and self.opts.collapse_affine else ""))
@@ -336,7 +343,7 @@ class _Emitter:
         for nid in hoist_front:
             w(f"        q.{self.nm(nid)} = {self.operand(nid, 'hoist')};")
         for nid in self.rcp_hoist:
-            w(f"        q.r{nid} = kem::rcp({self.operand(nid, 'hoist')});")
+            w(f"        q.r{nid} = 1.0 / {self.operand(nid, 'hoist')};")
         if not hoist_front and not self.rcp_hoist:
             w("        q.unused = 0.0; (void)p;")
         w("    }")
@@ -384,6 +391,12 @@ class _Emitter:
         uc = ", ".join(map(str, used_cols)) or "0"
         w(f"const int OUT_COLS[] = {{{oc}}};")
         w(f"const int USED_COLS[] = {{{uc}}};")
+        # output slots assigned a literal: nothing has to fetch them from the device
+        const_out = [(c, dag.fvalue(pm.out[c])) for c in self.out_cols if dag.is_const(pm.out[c])]
+        cc = ", ".join(str(c) for c, _ in const_out) or "0"
+        cv = ", ".join(_lit(v) for _, v in const_out) or "0.0"
+        w(f"const int CONST_OUT_COLS[] = {{{cc}}};")
+        w(f"const double CONST_OUT_VALS[] = {{{cv}}};")
         w("}  // namespace")
         w("")
         if self.const_table:
@@ -397,7 +410,8 @@ class _Emitter:
         # left out so that a generator release that emits the same code keeps the same hash
         code = "\n".join(ln for ln in body.split("\n") if not ln.startswith("// GENERATED by"))
         h = hashlib.sha256(code.encode()).hexdigest()[:16]
-        body += (f'\nKEM_DEFINE_MODEL(Model, "{name}", "{h}", OUT_COLS, USED_COLS, {len(used_cols)})\n')
+        body += (f'\nKEM_DEFINE_MODEL(Model, "{name}", "{h}", OUT_COLS, USED_COLS, {len(used_cols)}, '
+                 f'{len(const_out)}, CONST_OUT_COLS, CONST_OUT_VALS)\n')
 
         def count(order, ctx):
             c = {}

@@ -28,18 +28,92 @@ from __future__ import annotations
 import ctypes as C
 import os
 import time as _time
+import warnings
+import weakref
+from collections import OrderedDict
 
 import numpy as np
 
 from . import _cabi
 from ._cabi import (KEM_PARAM, KEM_SCHEME_DP45, KEM_SCHEME_RK4, KEM_STATE, KemError, NonFiniteStateError,
-                    check, kem_io_column, kem_step_times)
+                    StepControlError, check, kem_io_column, kem_step_times)
 from .codegen import EmitOptions, model_library
 
-__all__ = ["MembraneModel", "TableView", "KemError", "NonFiniteStateError"]
+__all__ = ["MembraneModel", "TableView", "KemError", "NonFiniteStateError", "StepControlError"]
 
 _SAMPLE_ROWS = 24
 _MASK_CACHE_ENTRIES = 8
+_STEP_CHUNKS = 16
+
+
+class _HostArrayCache:
+    """Page-locks caller arrays that keep coming back, without being asked to.
+
+    The reference's callers hand the SAME arrays to the getters every PDE step (`I_ch_k`,
+    `phi_M_prev`: utils.py:137-142, run_2D.py:105-109) and fresh ones to six of the seven
+    setters (`interpolate_to_membrane` creates its two Functions per call, utils.py:190-191).
+    Page-locking costs about as much as ten staged copies, so it pays for the first kind only:
+    an array is registered the second time the same memory arrives from the same, still living
+    owner object.  The owner check (a weak reference taken at the first sighting) tells a
+    persistent array from a new one that malloc happened to place at a recycled address.
+    Registered arrays are kept alive by a strong reference -- pinned pages must not be handed
+    back to the allocator -- and released least-recently-used first."""
+
+    def __init__(self, max_pinned=24, min_bytes=256 * 1024, max_seen=512):
+        self.max_pinned, self.min_bytes, self.max_seen = max_pinned, min_bytes, max_seen
+        self.seen = OrderedDict()      # (ptr, nbytes) -> weakref(owner)
+        self.pinned = OrderedDict()    # (ptr, nbytes) -> (owner, array)
+        self.refused = set()           # ranges the library would not register (overlap, foreign pin)
+
+    @staticmethod
+    def _ref(owner):
+        try:
+            return weakref.ref(owner)
+        except TypeError:
+            return None
+
+    def sight(self, owner, a) -> bool:
+        """Note that `a` (host memory of `owner`) takes part in an exchange; True if it is
+        page-locked by this cache afterwards."""
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.ndim == 1
+                and a.flags.c_contiguous and a.nbytes >= self.min_bytes):
+            return False
+        key = (a.ctypes.data, a.nbytes)
+        if key in self.pinned:
+            self.pinned.move_to_end(key)
+            return True
+        if key in self.refused:
+            return False
+        ref = self.seen.get(key)
+        if ref is not None and ref() is owner:
+            try:
+                check(_cabi.lib().kem_host_register(C.c_void_p(key[0]), key[1]), "kem_host_register")
+            except KemError:
+                self.refused.add(key)
+                return False
+            del self.seen[key]
+            self.pinned[key] = (owner, a)
+            while len(self.pinned) > self.max_pinned:
+                (ptr, _), _ = self.pinned.popitem(last=False)
+                _cabi.lib().kem_host_unregister(C.c_void_p(ptr))
+            return True
+        ref = self._ref(owner)
+        if ref is not None:
+            self.seen[key] = ref
+            self.seen.move_to_end(key)
+            while len(self.seen) > self.max_seen:
+                self.seen.popitem(last=False)
+        return False
+
+    def release_all(self):
+        for (ptr, _) in list(self.pinned):
+            _cabi.lib().kem_host_unregister(C.c_void_p(ptr))
+        self.pinned.clear()
+        self.seen.clear()
+        self.refused.clear()
+
+
+_HOST_CACHE = _HostArrayCache()
 
 
 def _default_devices():
@@ -150,9 +224,28 @@ class TableView:
 class MembraneModel:
     '''ODE on membrane defined by tagged facet function (B200 backend)'''
 
-    def __init__(self, ode, ft, tag, Q, *, devices=None, n_sub=25, scheme="rk4", rtol=1.0e-8,
-                 atol=1.0e-10, block=0, verbose=True, strict_locators=False,
-                 emit_options: EmitOptions | None = None, nvcc_flags=()):
+    def __init__(self, ode, ft, tag, Q, *, devices=None, n_sub=25, scheme="rk4", rtol=None,
+                 atol=None, block=0, verbose=True, strict_locators=False,
+                 emit_options: EmitOptions | None = None, nvcc_flags=(), unread_inputs="auto",
+                 exchange="immediate", auto_register=True):
+        """Keyword-only extensions of the reference's constructor ``(ode, ft, tag, Q)``:
+
+        scheme, n_sub     "rk4": fixed-step scheme O1 with `n_sub` sub-steps (no error control;
+                          the reference's LSODA controls the error at rtol 1e-8 / atol 1e-10);
+                          "dp45": error-controlled scheme O3 at `rtol` / `atol`.
+        unread_inputs     what a full-column write to a parameter the right-hand side never
+                          touches does: "auto" | "shadow" | "upload" | "discard"
+                          (KEM_UNREAD_* of include/knpemi_b200.h).
+        exchange          "immediate" (default): every setter copies when it is called and
+                          `step_lsoda` returns after the kernel, like the reference.
+                          "deferred": setters of page-locked arrays only record the array (it must
+                          not be modified before the step), `step_lsoda` runs the whole exchange as
+                          one chunk-pipelined enqueue and returns at once, the first getter waits
+                          for the kernel chunk by chunk; a failed integration is reported by that
+                          getter (or :meth:`synchronize`) instead of `step_lsoda`.
+        auto_register     page-lock caller arrays that come back a second time (see
+                          :class:`_HostArrayCache`); no effect on results.
+        """
         assert isinstance(tag, int)                                   # odeSolver.py:13
 
         # all DOFs of the membrane function space are stepped (odeSolver.py:32-38; `ft` unused)
@@ -167,6 +260,17 @@ class MembraneModel:
                              "Dormand-Prince 5(4) at rtol/atol)")
         self.scheme = scheme
         self._scheme_id = KEM_SCHEME_RK4 if scheme == "rk4" else KEM_SCHEME_DP45
+        if scheme == "rk4" and (rtol is not None or atol is not None):
+            warnings.warn("MembraneModel(scheme='rk4') is a fixed-step integrator: rtol/atol are ignored "
+                          "(accuracy is set by n_sub); pass scheme='dp45' for error control at the "
+                          "reference's LSODA tolerances", stacklevel=2)
+        rtol = 1.0e-8 if rtol is None else rtol                        # odeSolver.py:120
+        atol = 1.0e-10 if atol is None else atol
+        if unread_inputs not in _cabi.UNREAD_POLICIES:
+            raise ValueError(f"unread_inputs must be one of {sorted(_cabi.UNREAD_POLICIES)}")
+        if exchange not in ("immediate", "deferred"):
+            raise ValueError("exchange must be 'immediate' or 'deferred'")
+        self.unread_inputs, self.exchange, self.auto_register = unread_inputs, exchange, bool(auto_register)
         self.n_sub = int(n_sub)
         self.verbose = bool(verbose)
         self.strict_locators = bool(strict_locators)
@@ -198,6 +302,10 @@ class MembraneModel:
             check(self._lib.kem_set_block(self._h, int(block)), "kem_set_block")
         check(self._lib.kem_set_tolerances(self._h, float(rtol), float(atol)), "kem_set_tolerances")
         self.rtol, self.atol = float(rtol), float(atol)
+        check(self._lib.kem_set_unread_policy(self._h, _cabi.UNREAD_POLICIES[unread_inputs]),
+              "kem_set_unread_policy")
+        if exchange == "deferred":
+            check(self._lib.kem_set_step_chunks(self._h, _STEP_CHUNKS), "kem_set_step_chunks")
 
         self.states = TableView(self, KEM_STATE, self._ns)
         self.parameters = TableView(self, KEM_PARAM, self._np)
@@ -209,6 +317,8 @@ class MembraneModel:
 
         self._mask_cache = {}          # id(locator) -> (locator, mask)
         self._registered = []          # host arrays page-locked by register_host_array
+        self._pending = OrderedDict()  # exchange="deferred": (kind, col) -> (array, owner) not yet copied
+        self._status_pending = False   # an enqueue-only step whose status nobody has read yet
         self._stim_mask_key = "unset"
         self.last_step_times = None
 
@@ -219,7 +329,9 @@ class MembraneModel:
     def close(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            self._lib.kem_destroy(h)
+            self._lib.kem_destroy(h)                   # waits for the handle's streams
+        self._pending = OrderedDict()
+        self._inflight = None
         for a in getattr(self, "_registered", []):
             self._lib.kem_host_unregister(a.ctypes.data)
         self._registered = []
@@ -286,33 +398,76 @@ class MembraneModel:
         if self.verbose:
             print(f'\t{self.prefix} Stepping {self.nodes} ODEs')
         t_begin = _time.perf_counter()
-        flags = C.c_int(0)
-        if timed:
-            times = kem_step_times()
-            rc = self._lib.kem_step_timed(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
-                                          n_stim, cols, vals, C.byref(flags), C.byref(times))
-            self.last_step_times = {"ms_kernel": times.ms_kernel, "ms_total": times.ms_total,
-                                    "ms_h2d": times.ms_h2d, "ms_d2h": times.ms_d2h}
+        if self.exchange == "deferred" and not timed:
+            self._step_deferred(dt, n_sub, cols, vals, n_stim)
         else:
-            rc = self._lib.kem_step(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
-                                    n_stim, cols, vals, C.byref(flags))
-        check(rc, "kem_step")                                          # odeSolver.py:121
+            self._flush_pending()
+            flags = C.c_int(0)
+            if timed:
+                times = kem_step_times()
+                rc = self._lib.kem_step_timed(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
+                                              n_stim, cols, vals, C.byref(flags), C.byref(times))
+                self.last_step_times = {"ms_kernel": times.ms_kernel, "ms_total": times.ms_total,
+                                        "ms_h2d": times.ms_h2d, "ms_d2h": times.ms_d2h}
+            else:
+                rc = self._lib.kem_step(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
+                                        n_stim, cols, vals, C.byref(flags))
+            self._status_pending = False
+            check(rc, "kem_step")                                      # odeSolver.py:121
         self.time = self.time + dt                                     # odeSolver.py:106,123
         if self.verbose:
             print(f'\t{self.prefix} Stepped {self.nodes} ODES in {_time.perf_counter() - t_begin}s')
         return self.states
 
+    def _step_deferred(self, dt, n_sub, cols, vals, n_stim):
+        '''exchange="deferred": the recorded setter arrays go in, the step runs, all as one
+        chunk-pipelined enqueue (H2D of chunk c+1 under the kernel of chunk c); nothing waits.'''
+        pend, self._pending = self._pending, OrderedDict()
+        if pend:
+            arr = (kem_io_column * len(pend))()
+            for k, ((kind, col), (a, _owner)) in enumerate(pend.items()):
+                arr[k].kind, arr[k].col, arr[k].host = kind, col, a.ctypes.data
+            self._inflight = pend                  # keep the arrays alive until the copies are done
+            rc = self._lib.kem_step_io(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
+                                       n_stim, cols, vals, len(pend), arr, 0, None, None, None)
+            check(rc, "kem_step_io")
+        else:
+            check(self._lib.kem_step(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
+                                     n_stim, cols, vals, None), "kem_step")
+        self._status_pending = True
+
     def step_async(self, dt, stimulus=None, stimulus_locator=None, n_sub=None):
         '''Enqueue one step without waiting for it; errors surface at :meth:`synchronize`.'''
         cols, vals, n_stim = self._prepare_stimulus(stimulus, stimulus_locator)
         n_sub = self.n_sub if n_sub is None else int(n_sub)
+        self._flush_pending()
         check(self._lib.kem_step(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
                                  n_stim, cols, vals, None), "kem_step")
+        self._status_pending = True
         self.time = self.time + dt
         return self.states
 
     def synchronize(self):
+        '''Wait for everything enqueued; raises if an enqueue-only step failed.'''
+        self._flush_pending()
+        self._status_pending = False
+        self._inflight = None
         check(self._lib.kem_sync(self._h), "kem_sync")
+
+    def _flush_pending(self):
+        '''exchange="deferred": perform the recorded setter copies now (something other than a
+        step needs the tables to be current).'''
+        if self._pending:
+            pend, self._pending = self._pending, OrderedDict()
+            for (kind, col), (a, _owner) in pend.items():
+                self._set_column(kind, col, a[:self.nodes])
+
+    def _settle(self):
+        '''After a getter has waited for the device: report the status of an enqueue-only step.'''
+        if self._status_pending:
+            self._status_pending = False
+            self._inflight = None
+            check(self._lib.kem_sync(self._h), "kem_step")             # odeSolver.py:121, one call late
 
     def step_exchange(self, dt, inputs, outputs, stimulus=None, stimulus_locator=None, n_sub=None):
         '''One coupled PDE->ODE->PDE exchange in a single pipelined call.
@@ -324,6 +479,7 @@ class MembraneModel:
         Returns the CUDA-event timings of the exchange (ms).'''
         cols, vals, n_stim = self._prepare_stimulus(stimulus, stimulus_locator)
         n_sub = self.n_sub if n_sub is None else int(n_sub)
+        self._flush_pending()
         keep = []
 
         def pack(spec, writable):
@@ -331,6 +487,8 @@ class MembraneModel:
             for k, ((what, name), u) in enumerate(spec.items()):
                 kind, col = self._kind_col(what, name)
                 a = self._host_array(u, writable)
+                if self.auto_register:
+                    _HOST_CACHE.sight(u, a)
                 keep.append(a)
                 arr[k].kind, arr[k].col, arr[k].host = kind, col, a.ctypes.data
             return arr
@@ -341,6 +499,7 @@ class MembraneModel:
         rc = self._lib.kem_step_io(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
                                    n_stim, cols, vals, len(inputs), a_in, len(outputs), a_out,
                                    C.byref(flags), C.byref(times))
+        self._status_pending = False
         check(rc, "kem_step_io")
         self.time = self.time + dt
         self.last_step_times = {"ms_kernel": times.ms_kernel, "ms_total": times.ms_total,
@@ -354,7 +513,9 @@ class MembraneModel:
         step (utils.py:227-233, run_2D.py:105-109).  Ordinary (pageable) memory has to be copied
         through staging buffers; a registered array is read and written by the GPU's copy engine
         directly, so the unmodified call sequence moves at link speed.  The array is kept alive
-        and unregistered by :meth:`close`.  Returns `u`.'''
+        and released by :meth:`close` (registrations are reference-counted in the library: models
+        that register the same array share one page-lock).  Arrays that come back every step are
+        also registered automatically (`auto_register`); this call does it at once.  Returns `u`.'''
         a = u.x.array if hasattr(u, "x") else u
         if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.size > 0):
             raise KemError("register_host_array needs a non-empty contiguous float64 ndarray")
@@ -372,6 +533,7 @@ class MembraneModel:
     def gather_from_device(self, what, which, dev_ptr, map_id, shard=0):
         '''table[:, which] = bulk[map]  with `bulk` a device pointer: set_state/set_parameter
         without the host round trip.'''
+        self._flush_pending()
         kind, col = self._kind_col(what, which)
         check(self._lib.kem_device_gather(self._h, shard, kind, col, C.c_void_p(dev_ptr), int(map_id)),
               "kem_device_gather")
@@ -379,12 +541,14 @@ class MembraneModel:
 
     def scatter_to_device(self, what, which, dev_ptr, map_id, shard=0):
         '''bulk[map] = table[:, which]: get_state/get_parameter into a device vector.'''
+        self._flush_pending()
         kind, col = self._kind_col(what, which)
         check(self._lib.kem_device_scatter(self._h, shard, kind, col, C.c_void_p(dev_ptr), int(map_id)),
               "kem_device_scatter")
 
     def set_membrane_potential_from_device(self, phi_i_ptr, map_i, phi_e_ptr, map_e, shard=0):
         '''V = tr(phi_i) - tr(phi_e) on the device (update_pde_variables, utils.py:247-293).'''
+        self._flush_pending()
         kind, col = self._kind_col('state', 'V')
         check(self._lib.kem_device_gather_diff(self._h, shard, kind, col, C.c_void_p(phi_i_ptr), int(map_i),
                                                C.c_void_p(phi_e_ptr), int(map_e)), "kem_device_gather_diff")
@@ -407,6 +571,7 @@ class MembraneModel:
     def set_from_cuda_array(self, what, which, arr, shard=0):
         '''table[range of shard, which] = arr[:n_shard] for a CUDA array on that shard's device
         (device-to-device; no host round trip, no map).'''
+        self._flush_pending()
         kind, col = self._kind_col(what, which)
         n = self.shard_ranges()[shard][2] - self.shard_ranges()[shard][1]
         check(self._lib.kem_device_copy_in(self._h, shard, kind, col,
@@ -415,6 +580,7 @@ class MembraneModel:
 
     def get_to_cuda_array(self, what, which, arr, shard=0):
         '''arr[:n_shard] = table[range of shard, which] for a CUDA array on that shard's device.'''
+        self._flush_pending()
         kind, col = self._kind_col(what, which)
         n = self.shard_ranges()[shard][2] - self.shard_ranges()[shard][1]
         check(self._lib.kem_device_copy_out(self._h, shard, kind, col,
@@ -452,12 +618,12 @@ class MembraneModel:
         return a.value, r.value
 
     def column_location(self, what, which):
-        '''"uniform" | "device" | "host": where the column currently lives (a parameter the
-        right-hand side never touches stays in a host shadow).'''
+        '''"uniform" | "device" | "host" | "discarded": where the column currently lives (a
+        parameter the right-hand side never touches follows the `unread_inputs` policy).'''
         kind, col = self._kind_col(what, which)
         loc = C.c_int(-1)
         check(self._lib.kem_column_location(self._h, kind, col, C.byref(loc)), "kem_column_location")
-        return ("uniform", "device", "host")[loc.value]
+        return ("uniform", "device", "host", "discarded")[loc.value]
 
     def launch_count(self):
         n = C.c_int64(0)
@@ -515,8 +681,17 @@ class MembraneModel:
         if locator is None:
             return None
         hit = self._mask_cache.get(id(locator))
-        if hit is not None and hit[0] is locator:
-            return hit[1]
+        if hit is not None and hit[0] is locator and not self.strict_locators:
+            # The reference evaluates the locator on every row at every call (odeSolver.py:100,
+            # 140, 157).  The cached mask stands in for that only while the callable still
+            # answers the same on a sample of rows: a locator that closes over something the
+            # caller changes (a moving stimulus region) is re-evaluated, not served stale.
+            # `strict_locators=True` re-evaluates every row every time.
+            cached = hit[1]
+            rows = self._sample_rows(self.nodes)
+            X = self.dof_locations
+            if all(bool(locator(X[k])) == (True if cached is None else bool(cached[k])) for k in rows):
+                return cached
         mask = self._rows_of(locator)
         if mask.all():
             mask = None        # every row selected: same as no locator
@@ -573,24 +748,35 @@ class MembraneModel:
         return np.fromiter((float(get_value(x)) for x in X), dtype=np.float64, count=n)
 
     def _set_column(self, kind, col, src):
+        self._pending.pop((kind, col), None)            # a recorded write to this column is superseded
         check(self._lib.kem_set_column(self._h, kind, col, src.ctypes.data, self.nodes), "kem_set_column")
 
     def _get_column(self, kind, col, dst):
+        self._flush_pending()
         check(self._lib.kem_get_column(self._h, kind, col, dst.ctypes.data, self.nodes), "kem_get_column")
+        self._settle()
 
     # --- Work horses (odeSolver.py:130-188)
     def __set_ODE(self, what, which, u, locator=None):
         '''ODE setting '''
         kind, col = self._kind_col(what, which)
         mask = self._mask(locator)
-        source = np.ascontiguousarray(np.asarray(u.x.array[:])[:self.nodes], dtype=np.float64)
+        full = np.asarray(u.x.array)
+        source = np.ascontiguousarray(full[:self.nodes], dtype=np.float64)
         if len(source) < self.nodes:
             raise IndexError(f"u.x.array has {len(source)} entries, the membrane has {self.nodes} DOFs")
         if self.nodes == 0:
             return self.states
+        pinned = self.auto_register and _HOST_CACHE.sight(u, full)
         if mask is None:
-            self._set_column(kind, col, source)
+            if self.exchange == "deferred" and (pinned or _cabi.host_is_pinned(source)):
+                # only recorded: copied by the next step, pipelined with the kernel
+                self._pending.pop((kind, col), None)
+                self._pending[(kind, col)] = (source, u)
+            else:
+                self._set_column(kind, col, source)
         elif mask.any():
+            self._flush_pending()
             m8 = np.ascontiguousarray(mask, dtype=np.uint8)
             check(self._lib.kem_set_column_masked(self._h, kind, col, source.ctypes.data,
                                                   m8.ctypes.data, self.nodes), "kem_set_column_masked")
@@ -607,6 +793,8 @@ class MembraneModel:
                   and dest.ndim == 1 and dest.flags.c_contiguous and dest.flags.writeable
                   and len(dest) >= self.nodes)
         if direct:
+            if self.auto_register:
+                _HOST_CACHE.sight(u, dest)
             self._get_column(kind, col, dest)
             return u
         tmp = np.empty(self.nodes, dtype=np.float64)
@@ -622,6 +810,7 @@ class MembraneModel:
     def __set_ODE_values(self, what, value_dict, locator=None):
         '''Batch setter'''
         view = self.states if what == 'state' else self.parameters
+        self._flush_pending()
         mask = self._mask(locator)
         n_sel = self.nodes if mask is None else int(mask.sum())
         if self.verbose:

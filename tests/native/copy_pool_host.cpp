@@ -19,6 +19,21 @@ int main(int argc, char **argv)
             return 1;
         }
     }
+    // fills: zero (memset path) and a non-zero value, odd lengths
+    std::vector<double> d((n / 8) + 3, -1.0);
+    for (double v : {0.0, 2.5, -0.0}) {
+        const size_t len = d.size() - 3;
+        CopyPool::get().fill(d.data(), v, len);
+        for (size_t i = 0; i < len; ++i)
+            if (memcmp(&d[i], &v, sizeof v)) {
+                printf("FILL MISMATCH %g at %zu\n", v, i);
+                return 1;
+            }
+        if (d[len] != -1.0) {
+            printf("FILL OVERRUN\n");
+            return 1;
+        }
+    }
     CopyPool::get().copy(b.data(), a.data(), 0);
     CopyPool::get().copy(b.data(), a.data(), 17);
     printf("COPY_POOL_OK\n");

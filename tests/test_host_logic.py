@@ -72,3 +72,65 @@ def test_dof_sample_rows_cover_the_ends():
     m = bare_model(n=10_000)
     rows = m._sample_rows(10_000)
     assert rows[0] == 0 and rows[-1] == 9_999 and len(rows) <= 24
+
+
+def test_a_stateful_locator_is_not_served_from_the_cache():
+    """The reference re-evaluates the locator at every call (odeSolver.py:100): a callable whose
+    answer changes between calls must get a new mask, an unchanged one keeps its cached mask."""
+    m = bare_model(n=4000)
+    X = m.dof_locations
+    edge = {"x": 0.3}
+    loc = lambda x: x[0] < edge["x"]      # noqa: E731
+    first = m._mask(loc)
+    assert m._mask(loc) is first                                   # unchanged: cache hit
+    edge["x"] = 0.7
+    second = m._mask(loc)
+    assert second is not first and np.array_equal(second, X[:, 0] < 0.7)
+    edge["x"] = 2.0                                                # now selects everything
+    assert m._mask(loc) is None
+    edge["x"] = 0.1
+    assert np.array_equal(m._mask(loc), X[:, 0] < 0.1)
+
+
+def test_fixed_step_scheme_warns_about_ignored_tolerances():
+    """rtol/atol only act on scheme="dp45"; with the default fixed-step scheme they are ignored
+    and the constructor says so (the reference's LSODA call honours them, odeSolver.py:120)."""
+    from ducks_for_tests import Space
+    from knpemi_b200._cabi import KemError
+    from knpemi_b200.models import hh_test
+    import warnings
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        try:
+            m = MembraneModel(hh_test, None, 1, Space(np.zeros((4, 3))), verbose=False, rtol=1e-6)
+            m.close()
+        except KemError:
+            pass                                                   # no device on the CPU box
+    assert any("rtol/atol are ignored" in str(x.message) for x in w)
+    with pytest.raises(ValueError):
+        MembraneModel(hh_test, None, 1, Space(np.zeros((4, 3))), verbose=False, unread_inputs="maybe")
+    with pytest.raises(ValueError):
+        MembraneModel(hh_test, None, 1, Space(np.zeros((4, 3))), verbose=False, exchange="lazy")
+
+
+@pytest.mark.parametrize("n", [0, 1, 1000, 65536, 300_000, 1_000_000, 10_000_000, 50_000_000, 123_456_789])
+def test_chunk_plan_covers_the_range_and_tapers(n):
+    """The DOF chunks of the pipelined exchange: contiguous, complete, non-increasing, and the
+    last chunk is small so that the pipeline's drain (one kernel + one copy) is short."""
+    import ctypes as C
+    from knpemi_b200 import _cabi
+    off = (C.c_int64 * 128)()
+    ln = (C.c_int64 * 128)()
+    cnt = C.c_int(0)
+    _cabi.check(_cabi.lib().kem_plan_chunks(n, 16, off, ln, 128, C.byref(cnt)), "kem_plan_chunks")
+    k = cnt.value
+    if n == 0:
+        assert k == 0
+        return
+    assert 1 <= k <= 96
+    offs, lens = list(off[:k]), list(ln[:k])
+    assert offs[0] == 0 and all(offs[i] + lens[i] == offs[i + 1] for i in range(k - 1))
+    assert offs[-1] + lens[-1] == n and all(v > 0 for v in lens)
+    assert all(lens[i] >= lens[i + 1] for i in range(k - 2))       # (the very last one is the remainder)
+    if n >= 4_000_000:
+        assert lens[-1] <= 65536 and lens[0] >= n // 17 and max(lens) <= (n + 15) // 16 + 1024
