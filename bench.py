@@ -436,16 +436,19 @@ class Part:
 
 
 def measure_link(dev, dist):
-    """Host-link ceilings of this rank's GPU (pinned copies of 16 MB): alone, both directions,
-    and -- under torchrun -- with every rank of the box copying at the same time."""
+    """Host-link ceilings of this rank's GPU: pinned copies of 5 MB (one column chunk of the
+    exchange at 1e7 DOFs) streaming through 480 MB of host memory per direction -- alone, both
+    directions, and, under torchrun, with every rank of the box copying at the same time."""
     from knpemi_b200 import _cabi
-    nbytes, reps = 16 << 20, 16
-    out = {"copy_bytes": nbytes}
+    nbytes, reps, span = 5 << 20, 96, 480 << 20
+    out = {"copy_bytes": nbytes, "host_span_bytes_per_direction": span}
     if dist.rank == 0:
-        r = _cabi.link_ceiling(dev, nbytes, reps)
+        r = _cabi.link_ceiling(dev, nbytes, reps, span)
         out["one_gpu_alone"] = {k: round(v, 2) for k, v in r.items() if isinstance(v, float)}
+        c = _cabi.link_ceiling(dev, nbytes, reps, 0)
+        out["one_gpu_alone_cache_resident"] = {k: round(v, 2) for k, v in c.items() if isinstance(v, float)}
     dist.barrier()
-    h, d = _cabi.link_probe(dev, nbytes, 3 * reps, 3 * reps)
+    h, d = _cabi.link_probe(dev, nbytes, 2 * reps, 2 * reps, span)
     hs, ds = dist.gather(h), dist.gather(d)
     out["all_ranks_concurrent"] = {"h2d_per_rank": [round(v, 1) for v in hs], "d2h_per_rank": [round(v, 1) for v in ds],
                                    "h2d_sum": round(sum(hs), 1), "d2h_sum": round(sum(ds), 1)}

@@ -161,14 +161,16 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme,
                 int n_in, const kem_io_column *in, int n_out, const kem_io_column *out,
                 int *status_flags, kem_step_times *times_out);
 int kem_sync(kem_handle h);
-/* Launch the KEM_SCHEME_RK4 kernel of kem_step as `n_chunks` DOF chunks (tapered tail, two
+/* Launch the KEM_SCHEME_RK4 kernel of kem_step as `n_chunks` DOF chunks (two
  * compute streams) instead of one grid: a kem_get_column into page-locked memory that
  * follows then copies chunk c while chunk c+1 still computes.  1 (default) = one launch. */
 int kem_set_step_chunks(kem_handle h, int n_chunks);
 /* The DOF chunks kem_step_io / a chunked kem_step cut a range of n DOFs into (offsets and
- * lengths, at most `cap` written, the count always returned): `target` equal chunks whose tail
- * is tapered by halving so that the pipeline drains through a small last chunk.  No device needed. */
-int kem_plan_chunks(int64_t n, int target, int64_t *off_out, int64_t *len_out, int cap, int *count_out);
+ * lengths, at most `cap` written, the count always returned): `target` equal chunks; with
+ * taper = 1 the tail is halved repeatedly so that the pipeline drains through a small last
+ * chunk (taper = -1: the runtime's default, off unless KNPEMI_IO_TAPER=1).  No device needed. */
+int kem_plan_chunks(int64_t n, int target, int taper, int64_t *off_out, int64_t *len_out, int cap,
+                    int *count_out);
 /* tolerances of KEM_SCHEME_DP45; defaults are the reference's rtol 1e-8, atol 1e-10
  * (odeSolver.py:120) */
 int kem_set_tolerances(kem_handle h, double rtol, double atol);
@@ -209,6 +211,17 @@ int kem_device_gather_diff(kem_handle h, int shard, int kind, int col, const dou
                            int map_a, const double *dev_b, int map_b);
 /* contiguous device-to-device column copies for the DOFs of shard k (no map):
  * table[begin_k:end_k, col] = dev_src[0:n_k]   and   dev_dst[0:n_k] = table[begin_k:end_k, col] */
+/* out[i] = a0 + sum_k coef[k] * in_k[i] over a bulk vector of n DOFs on device `dev`: the
+ * eliminated-ion concentration of update_pde_variables (utils.py:247-267),
+ * c_elim = -(1/z_e) (rho_z rho_tag + sum_k z_k c_k), summed in the order given.  At most 8
+ * terms; synchronous on the default stream. */
+int kem_device_affine_combine(int dev, int64_t n, double *dev_out, double a0, int n_terms,
+                              const double *coef, const double *const *dev_in);
+/* table[i, col] = a0 + sum_k coef[k] * in_k[map[i]]: the membrane trace of that combination
+ * (what update_ode_variables pushes for the eliminated ion, utils.py:219-228) without forming
+ * the bulk vector first.  Enqueued on the handle's stream like kem_device_gather. */
+int kem_device_gather_affine(kem_handle h, int shard, int kind, int col, double a0, int n_terms,
+                             const double *coef, const double *const *dev_in, int map_id);
 int kem_device_copy_in(kem_handle h, int shard, int kind, int col, const double *dev_src);
 int kem_device_copy_out(kem_handle h, int shard, int kind, int col, double *dev_dst);
 /* plain device buffers for callers without their own CUDA allocations (tests, Python hosts) */
@@ -242,11 +255,13 @@ int kem_hbm_copy_peak(int dev, double *gbs_out);
 /* Host-link ceiling of device `dev`, the denominator of the end-to-end exchange
  * (the 7-in / 4-out column traffic of utils.py:217-233 + run_2D.py:105-109):
  * `reps_h2d` copies of `bytes` host->device and `reps_d2h` copies device->host run
- * concurrently on two streams from pinned memory of the calling thread; each
- * direction's elapsed milliseconds are returned (0 reps = that direction idle).
- * Unequal rep counts measure the shorter direction entirely under the other's load. */
-int kem_link_probe(int dev, size_t bytes, int reps_h2d, int reps_d2h, double *ms_h2d_out,
-                   double *ms_d2h_out);
+ * concurrently on two streams from pinned memory of the calling thread, walking through
+ * `span_bytes` of host memory per direction (0 = one buffer reused: cache-resident, the link
+ * alone; far above the last-level cache: through DRAM, like a real exchange).  Each direction's
+ * elapsed milliseconds are returned (0 reps = that direction idle).  Unequal rep counts measure
+ * the shorter direction entirely under the other's load. */
+int kem_link_probe(int dev, size_t bytes, size_t span_bytes, int reps_h2d, int reps_d2h,
+                   double *ms_h2d_out, double *ms_d2h_out);
 
 #ifdef __cplusplus
 }

@@ -88,12 +88,13 @@ kem_step_kernel(const __grid_constant__ KemArgs<M> a)
     constexpr int NS = M::NS, NOUT = M::NOUT, NT = M::NT;
     extern __shared__ double s_tt[];
 
-    // time-only factors of every stage time of this PDE step (host-evaluated)
+    // time-only factors of every stage time of this PDE step (host-evaluated), exp table
     if (NT > 0) {
         const int n_tt = (2 * a.n_sub + 2) * NT;
         for (int k = threadIdx.x; k < n_tt; k += BLOCK) s_tt[k] = a.ttab[k];
-        __syncthreads();
     }
+    kem::load_tables();
+    __syncthreads();
 
     const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (i >= a.n) return;
@@ -176,6 +177,8 @@ __global__ void __launch_bounds__(BLOCK)
 kem_step_dp45_kernel(const __grid_constant__ KemArgs<M> a)
 {
     constexpr int NS = M::NS, NOUT = M::NOUT, NT = M::NT;
+    kem::load_tables();
+    __syncthreads();
     const long long tid = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (tid >= a.n) return;
     // activity-sorted execution: neighbouring threads take DOFs that needed similar step

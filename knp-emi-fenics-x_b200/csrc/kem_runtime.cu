@@ -119,6 +119,63 @@ __global__ void k_gather_diff(double *__restrict__ dst, const double *__restrict
     for (; i < n; i += stride) dst[i] = a[map_a[i]] - b[map_b[i]];
 }
 
+// f3: out[i] = a0 + sum_k coef[k] * in_k[i], the eliminated-ion concentration of
+// update_pde_variables (utils.py:247-267): c_elim = -(1/z_e) (rho_z rho_tag + sum_k z_k c_k),
+// evaluated per bulk DOF in the order the sum is written.  Streaming and HBM-bound
+// (8 (n_terms + 1) bytes per DOF): double2 accesses when every pointer is 16-byte aligned.
+constexpr int KEM_MAX_TERMS = 8;
+struct AffineArgs {
+    double a0;
+    int n_terms;
+    double coef[KEM_MAX_TERMS];
+    const double *in[KEM_MAX_TERMS];
+};
+
+__global__ void k_affine_combine(double *__restrict__ out, const __grid_constant__ AffineArgs a, long long n,
+                                 int vec2)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (vec2) {
+        const long long n2 = n >> 1;
+        for (; i < n2; i += stride) {
+            double2 r = make_double2(a.a0, a.a0);
+            for (int k = 0; k < a.n_terms; ++k) {
+                const double2 v = reinterpret_cast<const double2 *>(a.in[k])[i];
+                r.x = r.x + a.coef[k] * v.x;
+                r.y = r.y + a.coef[k] * v.y;
+            }
+            reinterpret_cast<double2 *>(out)[i] = r;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) {
+            double r = a.a0;
+            for (int k = 0; k < a.n_terms; ++k) r = r + a.coef[k] * a.in[k][n - 1];
+            out[n - 1] = r;
+        }
+        return;
+    }
+    for (; i < n; i += stride) {
+        double r = a.a0;
+        for (int k = 0; k < a.n_terms; ++k) r = r + a.coef[k] * a.in[k][i];
+        out[i] = r;
+    }
+}
+
+// the same combination taken at the bulk DOF of every membrane DOF: the trace of the
+// eliminated ion lands in a table column without the bulk vector being formed first
+__global__ void k_gather_affine(double *__restrict__ dst, const __grid_constant__ AffineArgs a,
+                                const long long *__restrict__ map, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const long long j = map[i];
+        double r = a.a0;
+        for (int k = 0; k < a.n_terms; ++k) r = r + a.coef[k] * a.in[k][j];
+        dst[i] = r;
+    }
+}
+
 // ---- activity sort for scheme O3 (error-controlled stepping) ---------------------------
 // bucket = quarter-octaves of dt/hsug (about the number of steps the DOF took last time),
 // 0 for a DOF that has no history; 64 buckets cover up to 2^16 steps per PDE step.
@@ -237,6 +294,7 @@ struct Shard {
     int dev = 0;
     int64_t begin = 0, n = 0;
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_in2 = nullptr;     // optional second host->device stream (KNPEMI_IO_H2D_STREAMS=2)
     cudaStream_t stream2 = nullptr;   // second compute stream: chunk kernels of kem_step_io alternate
                                       // between the two so one chunk's tail overlaps the next one's head
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
@@ -259,7 +317,7 @@ struct Shard {
     void *h_stage[N_STAGE] = {};
     cudaEvent_t stage_ev[N_STAGE] = {};
     // per-chunk events of kem_step_io / a chunked kem_step
-    std::vector<cudaEvent_t> io_in, io_k0, io_k1, io_out;
+    std::vector<cudaEvent_t> io_in, io_k0, io_k1, io_out, io_in2;
     // DOF chunks of the last chunked step; `chunks_live` while nothing else has been enqueued
     // since, so that a getter may follow the kernel chunk by chunk instead of waiting for all
     std::vector<int64_t> ch_off, ch_len;
@@ -538,6 +596,7 @@ int sync_all(kem_handle h)
     for (Shard &s : h->shards) {
         CK(cudaSetDevice(s.dev));
         CK(cudaStreamSynchronize(s.s_in));
+        CK(cudaStreamSynchronize(s.s_in2));
         CK(cudaStreamSynchronize(s.stream2));
         CK(cudaStreamSynchronize(s.stream));
         CK(cudaStreamSynchronize(s.s_out));
@@ -563,20 +622,28 @@ void build_ttab(const KemModelDesc *m, double t0, double dt, int n_sub, std::vec
     m->tonly(t0 + dt, &tab[(size_t)(2 * n_sub + 1) * nt]);
 }
 
-// DOF chunks of one pipelined exchange (kem_step_io) or of a chunked kem_step.  The body of
-// the range is cut into `target` equal chunks (each launch still fills the GPU for several
-// waves, each column copy is several MB); the tail is tapered: whenever at most four chunks
-// of the current size remain the size is halved, down to IO_MIN_CHUNK, so that the pipeline
-// drains through a small last chunk (kernel + copy of 64k DOFs) instead of a sixteenth of
-// the range.  KNPEMI_IO_TAPER=0 restores equal chunks.
-void plan_chunks(int64_t n, int target, std::vector<int64_t> &off, std::vector<int64_t> &len)
+// DOF chunks of one pipelined exchange (kem_step_io) or of a chunked kem_step: `target` equal
+// chunks (each launch still fills the GPU for several waves, each column copy is several MB).
+// With `taper` the tail is cut finer -- whenever at most four chunks of the current size
+// remain the size is halved, down to IO_MIN_CHUNK -- so that the pipeline drains through a
+// small last chunk.  Measured on B200 (profiles/r2_exchange.md): the drain it saves (0.5 ms of
+// 10) is less than what the small copies cost, because a copy of 1 MB moves at 32 GB/s when
+// both directions are busy and one of 5 MB at 48; equal chunks are the default,
+// KNPEMI_IO_TAPER=1 turns the taper on.
+bool taper_default()
+{
+    static const bool on = getenv("KNPEMI_IO_TAPER") && atoi(getenv("KNPEMI_IO_TAPER")) != 0;
+    return on;
+}
+
+void plan_chunks(int64_t n, int target, std::vector<int64_t> &off, std::vector<int64_t> &len,
+                 bool taper = taper_default())
 {
     off.clear();
     len.clear();
     if (n <= 0) return;
     if (const char *e = getenv("KNPEMI_IO_CHUNKS")) target = atoi(e);
     target = std::max(1, std::min(target, IO_MAX_CHUNKS / 2));
-    static const bool taper = !(getenv("KNPEMI_IO_TAPER") && atoi(getenv("KNPEMI_IO_TAPER")) == 0);
     int64_t chunk = std::max<int64_t>((n + target - 1) / target, 2 * IO_MIN_CHUNK);
     chunk = (chunk + 1023) / 1024 * 1024;
     int64_t at = 0;
@@ -603,6 +670,7 @@ int ensure_chunk_events(Shard &s, size_t n_chunks)
         CK(cudaEventCreate(&e)); s.io_k0.push_back(e);
         CK(cudaEventCreate(&e)); s.io_k1.push_back(e);
         CK(cudaEventCreate(&e)); s.io_out.push_back(e);
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); s.io_in2.push_back(e);
     }
     return KEM_OK;
 }
@@ -1033,6 +1101,7 @@ int kem_create(int model_id, int64_t n_dof, int n_dev, const int *dev_ids,
         CKB(cudaSetDevice(s.dev));
         CKB(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CKB(cudaStreamCreateWithFlags(&s.s_in, cudaStreamNonBlocking));
+        CKB(cudaStreamCreateWithFlags(&s.s_in2, cudaStreamNonBlocking));
         CKB(cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
         CKB(cudaStreamCreateWithFlags(&s.s_out, cudaStreamNonBlocking));
         CKB(cudaEventCreate(&s.ev_a));
@@ -1079,6 +1148,7 @@ int kem_destroy(kem_handle h)
         if (cudaSetDevice(s.dev) != cudaSuccess) continue;
         if (s.stream) cudaStreamSynchronize(s.stream);
         if (s.s_in) cudaStreamSynchronize(s.s_in);
+        if (s.s_in2) cudaStreamSynchronize(s.s_in2);
         if (s.stream2) cudaStreamSynchronize(s.stream2);
         if (s.s_out) cudaStreamSynchronize(s.s_out);
         for (double *p : s.ycol) if (p) cudaFree(p);
@@ -1102,11 +1172,12 @@ int kem_destroy(kem_handle h)
             if (s.h_stage[r]) cudaFreeHost(s.h_stage[r]);
             if (s.stage_ev[r]) cudaEventDestroy(s.stage_ev[r]);
         }
-        for (auto *v : {&s.io_in, &s.io_k0, &s.io_k1, &s.io_out})
+        for (auto *v : {&s.io_in, &s.io_k0, &s.io_k1, &s.io_out, &s.io_in2})
             for (cudaEvent_t e : *v) cudaEventDestroy(e);
         for (cudaEvent_t e : {s.ev_a, s.ev_b, s.ev_c, s.ev_d, s.ev_t0, s.ev_t1}) if (e) cudaEventDestroy(e);
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.s_in) cudaStreamDestroy(s.s_in);
+        if (s.s_in2) cudaStreamDestroy(s.s_in2);
         if (s.stream2) cudaStreamDestroy(s.stream2);
         if (s.s_out) cudaStreamDestroy(s.s_out);
     }
@@ -1636,11 +1707,19 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
         CK(cudaStreamWaitEvent(s.stream2, s.ev_a, 0));
         CK(cudaStreamWaitEvent(s.s_out, s.ev_a, 0));
         CK(cudaEventRecord(s.ev_b, s.s_in));   // t = 0 of this shard's exchange
+        // (experiment knob: spread the input columns over two copy streams)
+        static const bool two_in = getenv("KNPEMI_IO_H2D_STREAMS") && atoi(getenv("KNPEMI_IO_H2D_STREAMS")) == 2;
+        if (two_in) CK(cudaStreamWaitEvent(s.s_in2, s.ev_a, 0));
         for (size_t c = 0; c < n_chunks; ++c) {
             for (int k = 0; k < n_in; ++k)
                 CK(cudaMemcpyAsync(col_ptr(s, in[k].kind, in[k].col) + s.ch_off[c],
                                    in[k].host + s.begin + s.ch_off[c],
-                                   (size_t)s.ch_len[c] * sizeof(double), cudaMemcpyHostToDevice, s.s_in));
+                                   (size_t)s.ch_len[c] * sizeof(double), cudaMemcpyHostToDevice,
+                                   (two_in && (k & 1)) ? s.s_in2 : s.s_in));
+            if (two_in) {
+                CK(cudaEventRecord(s.io_in2[c], s.s_in2));
+                CK(cudaStreamWaitEvent(s.s_in, s.io_in2[c], 0));
+            }
             CK(cudaEventRecord(s.io_in[c], s.s_in));
         }
         rc = launch_chunked(h, s, pl, s.io_in.data());
@@ -1709,11 +1788,12 @@ int kem_set_unread_policy(kem_handle h, int policy)
     return KEM_OK;
 }
 
-int kem_plan_chunks(int64_t n, int target, int64_t *off_out, int64_t *len_out, int cap, int *count_out)
+int kem_plan_chunks(int64_t n, int target, int taper, int64_t *off_out, int64_t *len_out, int cap,
+                    int *count_out)
 {
     ARG(count_out && n >= 0, "bad arguments");
     std::vector<int64_t> off, len;
-    plan_chunks(n, target, off, len);
+    plan_chunks(n, target, off, len, taper < 0 ? taper_default() : taper != 0);
     *count_out = (int)off.size();
     for (int k = 0; k < std::min<int>(cap, (int)off.size()); ++k) {
         if (off_out) off_out[k] = off[k];
@@ -1891,6 +1971,68 @@ int kem_device_gather_diff(kem_handle h, int shard, int kind, int col, const dou
     CK(cudaSetDevice(s.dev));
     k_gather_diff<<<grid_for(s.n), 256, 0, s.stream>>>(col_ptr(s, kind, col), dev_a, s.d_map[map_a],
                                                        dev_b, s.d_map[map_b], s.n);
+    CK(cudaGetLastError());
+    h->launches++;
+    return KEM_OK;
+}
+
+static int fill_affine(AffineArgs &a, double a0, int n_terms, const double *coef,
+                       const double *const *dev_in, const char *fn)
+{
+    if (n_terms < 0 || n_terms > KEM_MAX_TERMS || (n_terms && (!coef || !dev_in)))
+        return fail(KEM_E_ARG, std::string(fn) + ": 0.." + std::to_string(KEM_MAX_TERMS) + " terms");
+    memset(&a, 0, sizeof a);
+    a.a0 = a0;
+    a.n_terms = n_terms;
+    for (int k = 0; k < n_terms; ++k) {
+        if (!dev_in[k]) return fail(KEM_E_ARG, std::string(fn) + ": null device pointer");
+        a.coef[k] = coef[k];
+        a.in[k] = dev_in[k];
+    }
+    return KEM_OK;
+}
+
+int kem_device_affine_combine(int dev, int64_t n, double *dev_out, double a0, int n_terms,
+                              const double *coef, const double *const *dev_in)
+{
+    ARG(n >= 0 && (dev_out || n == 0), "bad output");
+    AffineArgs a;
+    int rc = fill_affine(a, a0, n_terms, coef, dev_in, __func__);
+    if (rc) return rc;
+    if (n == 0) return KEM_OK;
+    CK(cudaSetDevice(dev));
+    bool aligned = ((uintptr_t)dev_out & 15) == 0;
+    for (int k = 0; k < n_terms; ++k) aligned = aligned && ((uintptr_t)dev_in[k] & 15) == 0;
+    // legacy default stream: ordered after the caller's earlier default-stream work
+    k_affine_combine<<<grid_for(aligned ? n / 2 + 1 : n), 256>>>(dev_out, a, n, aligned ? 1 : 0);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(0));
+    return KEM_OK;
+}
+
+int kem_device_gather_affine(kem_handle h, int shard, int kind, int col, double a0, int n_terms,
+                             const double *coef, const double *const *dev_in, int map_id)
+{
+    int rc = device_xfer_check(h, shard, kind, col, n_terms > 0 && dev_in ? dev_in[0] : (const void *)h, map_id,
+                               __func__);
+    if (rc) return rc;
+    AffineArgs a;
+    rc = fill_affine(a, a0, n_terms, coef, dev_in, __func__);
+    if (rc) return rc;
+    touch_param(h, kind, col);
+    drop_live_chunks(h);
+    if (kind == KEM_PARAM && not_on_device(h, col)) {
+        if (h->p_discarded[col]) {                 // every row is overwritten below
+            h->p_discarded[col] = 0;
+            h->p_uniform[col] = 1;
+        }
+        rc = ensure_pcol(h, col);
+        if (rc) return rc;
+    }
+    Shard &s = h->shards[shard];
+    if (s.n == 0) return KEM_OK;
+    CK(cudaSetDevice(s.dev));
+    k_gather_affine<<<grid_for(s.n), 256, 0, s.stream>>>(col_ptr(s, kind, col), a, s.d_map[map_id], s.n);
     CK(cudaGetLastError());
     h->launches++;
     return KEM_OK;
@@ -2113,20 +2255,27 @@ int kem_fp64_peak(int dev, double *tflops_out, double *ms_out)
 
 // Host-link ceiling of device `dev`: `reps_h2d` copies of `bytes` host->device on one stream
 // and `reps_d2h` copies device->host on another, enqueued interleaved (start skew ~10 us), pinned
-// host memory allocated by the calling thread (so its NUMA placement is the bench's).
-// A direction's elapsed time is first copy start -> its last copy end.  With unequal rep
-// counts the shorter direction is measured entirely under the other one's traffic.
-int kem_link_probe(int dev, size_t bytes, int reps_h2d, int reps_d2h, double *ms_h2d_out,
-                   double *ms_d2h_out)
+// host memory allocated by the calling thread (so its NUMA placement is the bench's).  Successive
+// copies walk through `span_bytes` of host memory per direction (0 = reuse one buffer): with a
+// span far above the CPU's last-level cache the copies stream through DRAM like the exchange
+// of a real PDE step does; with one small buffer they are served from the cache (DDIO) and show
+// the PCIe link alone.  A direction's elapsed time is first copy start -> its last copy end.
+// With unequal rep counts the shorter direction is measured entirely under the other's traffic.
+int kem_link_probe(int dev, size_t bytes, size_t span_bytes, int reps_h2d, int reps_d2h,
+                   double *ms_h2d_out, double *ms_d2h_out)
 {
     ARG(bytes >= 8 && reps_h2d >= 0 && reps_d2h >= 0 && reps_h2d + reps_d2h > 0, "bad probe size");
     ARG(ms_h2d_out && ms_d2h_out, "null output");
+    if (span_bytes < bytes) span_bytes = bytes;
+    const size_t slots = span_bytes / bytes;
+    span_bytes = slots * bytes;
     CK(cudaSetDevice(dev));
-    void *h_a = nullptr, *h_b = nullptr, *d_a = nullptr, *d_b = nullptr;
-    CK(cudaHostAlloc(&h_a, bytes, cudaHostAllocDefault));
-    CK(cudaHostAlloc(&h_b, bytes, cudaHostAllocDefault));
-    memset(h_a, 1, bytes);
-    memset(h_b, 2, bytes);
+    char *h_a = nullptr, *h_b = nullptr;
+    void *d_a = nullptr, *d_b = nullptr;
+    CK(cudaHostAlloc((void **)&h_a, span_bytes, cudaHostAllocDefault));
+    CK(cudaHostAlloc((void **)&h_b, span_bytes, cudaHostAllocDefault));
+    CopyPool::get().fill((double *)h_a, 1.0, span_bytes / sizeof(double));     // touch every page
+    CopyPool::get().fill((double *)h_b, 2.0, span_bytes / sizeof(double));
     CK(cudaMalloc(&d_a, bytes));
     CK(cudaMalloc(&d_b, bytes));
     CK(cudaMemset(d_b, 0, bytes));
@@ -2146,8 +2295,9 @@ int kem_link_probe(int dev, size_t bytes, int reps_h2d, int reps_d2h, double *ms
     CK(cudaEventRecord(i0, s_in));
     CK(cudaEventRecord(o0, s_out));
     for (int k = 0; k < std::max(reps_h2d, reps_d2h); ++k) {      // interleaved enqueue
-        if (k < reps_h2d) CK(cudaMemcpyAsync(d_a, h_a, bytes, cudaMemcpyHostToDevice, s_in));
-        if (k < reps_d2h) CK(cudaMemcpyAsync(h_b, d_b, bytes, cudaMemcpyDeviceToHost, s_out));
+        const size_t off = ((size_t)k % slots) * bytes;
+        if (k < reps_h2d) CK(cudaMemcpyAsync(d_a, h_a + off, bytes, cudaMemcpyHostToDevice, s_in));
+        if (k < reps_d2h) CK(cudaMemcpyAsync(h_b + off, d_b, bytes, cudaMemcpyDeviceToHost, s_out));
     }
     CK(cudaEventRecord(i1, s_in));
     CK(cudaEventRecord(o1, s_out));

@@ -88,7 +88,8 @@ SIGNATURES = {
     "kem_sync": (C.c_int, [_H]),
     "kem_set_unread_policy": (C.c_int, [_H, C.c_int]),
     "kem_set_step_chunks": (C.c_int, [_H, C.c_int]),
-    "kem_plan_chunks": (C.c_int, [C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int, _IP]),
+    "kem_plan_chunks": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                  C.c_int, _IP]),
     "kem_set_tolerances": (C.c_int, [_H, C.c_double, C.c_double]),
     "kem_set_activity_sort": (C.c_int, [_H, C.c_int]),
     "kem_get_step_stats": (C.c_int, [_H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -101,6 +102,10 @@ SIGNATURES = {
     "kem_device_scatter": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "kem_device_gather_diff": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                          C.c_int]),
+    "kem_device_affine_combine": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_int, _DP,
+                                            C.POINTER(C.c_void_p)]),
+    "kem_device_gather_affine": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, _DP,
+                                           C.POINTER(C.c_void_p), C.c_int]),
     "kem_device_copy_in": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "kem_device_copy_out": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "kem_device_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -114,7 +119,7 @@ SIGNATURES = {
     "kem_host_is_pinned": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "kem_fp64_peak": (C.c_int, [C.c_int, _DP, _DP]),
     "kem_hbm_copy_peak": (C.c_int, [C.c_int, _DP]),
-    "kem_link_probe": (C.c_int, [C.c_int, C.c_size_t, C.c_int, C.c_int, _DP, _DP]),
+    "kem_link_probe": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, _DP, _DP]),
 }
 
 _lib = None
@@ -222,24 +227,28 @@ def hbm_copy_peak(dev: int = 0) -> float:
     return g.value
 
 
-def link_probe(dev: int, nbytes: int, reps_h2d: int, reps_d2h: int) -> tuple[float, float]:
-    """(GB/s host->device, GB/s device->host) of `reps_*` concurrent pinned copies of `nbytes`."""
+def link_probe(dev: int, nbytes: int, reps_h2d: int, reps_d2h: int, span: int = 0) -> tuple[float, float]:
+    """(GB/s host->device, GB/s device->host) of `reps_*` concurrent pinned copies of `nbytes`
+    walking through `span` bytes of host memory per direction (0: one cache-resident buffer)."""
     a, b = C.c_double(), C.c_double()
-    check(lib().kem_link_probe(dev, nbytes, reps_h2d, reps_d2h, C.byref(a), C.byref(b)), "kem_link_probe")
+    check(lib().kem_link_probe(dev, nbytes, span, reps_h2d, reps_d2h, C.byref(a), C.byref(b)), "kem_link_probe")
     return (nbytes * reps_h2d / (a.value * 1e-3) / 1e9 if reps_h2d else 0.0,
             nbytes * reps_d2h / (b.value * 1e-3) / 1e9 if reps_d2h else 0.0)
 
 
-def link_ceiling(dev: int = 0, nbytes: int = 64 << 20, reps: int = 12) -> dict:
+def link_ceiling(dev: int = 0, nbytes: int = 5 << 20, reps: int = 96, span: int = 480 << 20) -> dict:
     """Measured pinned-copy ceilings of one GPU's host link, GB/s per direction: each direction
-    alone, both saturated, and each direction while the other one runs for twice as long."""
-    h_alone, _ = link_probe(dev, nbytes, reps, 0)
-    _, d_alone = link_probe(dev, nbytes, 0, reps)
-    h_both, d_both = link_probe(dev, nbytes, reps, reps)
-    h_loaded, _ = link_probe(dev, nbytes, reps, 2 * reps)
-    _, d_loaded = link_probe(dev, nbytes, 2 * reps, reps)
+    alone, both saturated, and each direction while the other one runs for twice as long.
+    Defaults: 5 MB copies (one column chunk of the pipelined exchange at 1e7 DOFs) streaming
+    through 480 MB of host memory per direction (far above the last-level cache)."""
+    h_alone, _ = link_probe(dev, nbytes, reps, 0, span)
+    _, d_alone = link_probe(dev, nbytes, 0, reps, span)
+    h_both, d_both = link_probe(dev, nbytes, reps, reps, span)
+    h_loaded, _ = link_probe(dev, nbytes, reps, 2 * reps, span)
+    _, d_loaded = link_probe(dev, nbytes, 2 * reps, reps, span)
     return {"h2d_alone": h_alone, "d2h_alone": d_alone, "h2d_both": h_both, "d2h_both": d_both,
-            "h2d_under_d2h": h_loaded, "d2h_under_h2d": d_loaded, "copy_bytes": nbytes, "reps": reps}
+            "h2d_under_d2h": h_loaded, "d2h_under_h2d": d_loaded, "copy_bytes": nbytes, "reps": reps,
+            "span_bytes": span}
 
 
 class DeviceArray:

@@ -24,7 +24,7 @@ from dataclasses import dataclass
 from .ir import P, S, T, Dag, ModelSourceError
 from .parse import ParsedModel
 
-CODEGEN_VERSION = "11"
+CODEGEN_VERSION = "12"
 
 
 @dataclass
@@ -51,6 +51,13 @@ class EmitOptions:
     max_exp_power: int = 96
     #: also share exponentials whose offset depends on parameters (hoisted exp(offset); unbounded)
     fuse_exp_param_offsets: bool = False
+    #: "fast" only: a/b -> a*rcp(b) (1.5 ulp, 4 FP64 instructions) instead of the residual-corrected
+    #: kem::div (0.5 ulp, 6 instructions) for in-loop divisions by state-dependent values; nothing in
+    #: the path amplifies a quotient's last bit (the removable singularities amplify the error of
+    #: exp(x) - 1, which both forms receive unchanged)
+    exact_div: bool = os.environ.get("KNPEMI_EXACT_DIV", "0") == "1"
+    #: "fast" only: a*(1 - x) - b*x -> a - x*(a + b) (codegen/relax.py)
+    relax_gates: bool = os.environ.get("KNPEMI_RELAX_GATES", "1") != "0"
     #: "fast" only, experimental (off): chains of affine operations on one node collapse into one
     #: FMA of that node (codegen/affine.py); checked on the CPU, not yet measured on the device
     collapse_affine: bool = os.environ.get("KNPEMI_COLLAPSE_AFFINE", "0") == "1"
@@ -184,7 +191,9 @@ class _Emitter:
                     if self.dag.fvalue(num) == 1.0:
                         return f"kem::rcp({a[1]})"
                     return f"{a[0]} * kem::rcp({a[1]})"
-                return f"kem::div({a[0]}, {a[1]})"
+                if self.opts.exact_div:
+                    return f"kem::div({a[0]}, {a[1]})"
+                return f"{a[0]} * kem::rcp({a[1]})"
             return f"{a[0]} / {a[1]}"
         if op == "neg":
             return f"-{a[0]}"
@@ -309,6 +318,7 @@ class _Emitter:
         w(f"// model {name!r} from {shown}:{pm.lineno}")
         w(f"// options: default_block={self.opts.default_block} math={self.opts.math}"
           f" fuse_exp={int(self.fast and self.opts.fuse_exp)}"
+          f" exact_div={int(self.opts.exact_div)} relax_gates={int(self.fast and self.opts.relax_gates)}"
           + (" collapse_affine=1" if self.fast and self.opts.collapse_affine else ""))
         w('#include <math.h>')
         w('#include "kem_math.cuh"')
@@ -440,6 +450,10 @@ def emit_model(pm: ParsedModel, name: str, ns: int, np_: int, opts: EmitOptions 
     if opts.math == "fast" and opts.fuse_exp:
         from .fuse_exp import fuse_exponentials
         pm, fused = fuse_exponentials(pm, opts.max_exp_power, opts.fuse_exp_param_offsets)
+    relaxed = []
+    if opts.math == "fast" and opts.relax_gates:
+        from .relax import relax_gates
+        pm, relaxed = relax_gates(pm)
     collapsed = []
     if opts.math == "fast" and opts.collapse_affine:
         from .affine import collapse_affine
@@ -447,4 +461,5 @@ def emit_model(pm: ParsedModel, name: str, ns: int, np_: int, opts: EmitOptions 
     em = _Emitter(pm, ns, np_, opts).emit(name)
     em.stats["fused_exp"] = fused
     em.stats["collapsed_affine"] = collapsed
+    em.stats["relaxed_gates"] = relaxed
     return em

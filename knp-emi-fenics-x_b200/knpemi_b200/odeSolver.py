@@ -554,6 +554,18 @@ class MembraneModel:
                                                C.c_void_p(phi_e_ptr), int(map_e)), "kem_device_gather_diff")
         return self.states
 
+    def set_from_device_affine(self, what, which, a0, terms, map_id, shard=0):
+        '''table[:, which] = a0 + sum_k coef_k * bulk_k[map]  with `terms` = [(coef_k, device
+        pointer of bulk_k)]: the membrane trace of the eliminated-ion concentration
+        (utils.py:247-267 followed by utils.py:219-228) without forming the bulk vector.'''
+        from .device_updates import _pack
+        self._flush_pending()
+        kind, col = self._kind_col(what, which)
+        coef, ptrs = _pack(terms)
+        check(self._lib.kem_device_gather_affine(self._h, shard, kind, col, float(a0), len(terms), coef, ptrs,
+                                                 int(map_id)), "kem_device_gather_affine")
+        return self.states
+
     @staticmethod
     def _cuda_pointer(arr, n, writable):
         '''Device pointer of a CUDA array (torch.cuda / CuPy / Numba: __cuda_array_interface__).'''

@@ -64,7 +64,13 @@ def test_math_modes_emit_different_code():
     fast = codegen.generate(ode, EmitOptions(math="fast")).source
     libm = codegen.generate(ode, EmitOptions(math="libm")).source
     assert "kem::exp(" in fast and "kem::exp(" not in libm
-    assert "kem::div(" in fast and " / " in libm
+    assert "kem::rcp(" in fast and "kem::div(" not in fast and " / " in libm
+    exact = codegen.generate(ode, EmitOptions(math="fast", exact_div=True)).source
+    assert "kem::div(" in exact
+    # a*(1 - x) - b*x is emitted as a - x*(a + b) unless asked not to
+    plain = codegen.generate(ode, EmitOptions(math="fast", relax_gates=False))
+    assert len(codegen.generate(ode).stats["relaxed_gates"]) == 3 and not plain.stats["relaxed_gates"]
+    assert plain.stats["deriv"]["sub"] > codegen.generate(ode).stats["deriv"]["sub"]
     with pytest.raises(ValueError):
         codegen.generate(ode, EmitOptions(math="wrong"))
 
@@ -400,3 +406,27 @@ def test_affine_collapse_is_off_by_default_and_changes_the_source_when_on():
     assert on.source_hash != off.source_hash
     loop = on.source[on.source.index("void deriv"):on.source.index("void outputs")]
     assert "// u" not in loop            # the rescaled potential u = 1e3*(V + 65e-3) is gone
+
+
+def test_relaxed_gate_form_is_the_same_function():
+    """codegen/relax.py: `a*(1 - x) - b*x -> a - x*(a + b)` on the DAG, checked with the
+    interpreter on random points (equal up to the rounding of three operations)."""
+    from knpemi_b200.codegen.interpret import evaluate
+    from knpemi_b200.codegen.relax import relax_gates
+    body = [
+        "a = np.exp(states[1])",
+        "b = parameters[0] * states[1] + 2.0",
+        "values[0] = a * (1 - states[0]) - b * states[0]",
+        "values[1] = (1.0 - states[1]) * b - states[1] * a",       # factors in the other order
+        "parameters[1] = a * (1 - states[0]) - b * states[1]",      # not the pattern: different x
+    ]
+    pm = parse_model_source(_src(body))
+    pm2, report = relax_gates(pm)
+    assert len(report) == 2
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        y = list(rng.uniform(0.01, 0.99, 2))
+        p = [float(rng.uniform(0.5, 2.0)), 0.0]
+        dy1, p1 = evaluate(pm, 0.0, y, list(p))
+        dy2, p2 = evaluate(pm2, 0.0, y, list(p))
+        assert np.allclose(dy1, dy2, rtol=1e-15, atol=1e-15) and p1[1] == p2[1]

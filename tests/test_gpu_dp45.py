@@ -129,3 +129,36 @@ def test_activity_sorted_execution_does_not_change_results(built):
         m.close()
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     assert res[0][2] == res[1][2]
+
+
+@pytest.mark.parametrize("name", ["hh_tissue", "hh_ideal", "glial_tissue", "calibration"])
+def test_device_dp45_against_lsoda_at_the_reference_tolerances(built, name):
+    """Row f2, "validated against O2": the device integrator against LSODA itself -- scipy's,
+    standing in for numbalsoda -- at the reference's rtol 1e-8 / atol 1e-10, cold-started per row
+    and per PDE step like odeSolver.py:116-120, through the same right-hand side.  Both are
+    error-controlled at the same tolerances, so they agree at the level either agrees with a
+    tight solution (RK4 x 800); nothing pins LSODA's own error more tightly than that."""
+    from knpemi_b200.odeSolver import MembraneModel
+    from oracle.membrane_oracle import OracleMembraneModel
+    n = 12
+    ode = builtin(name)
+    cfg = SETUP[name]
+    S, P, X, mask = synthetic_tables(name, n, seed=3)
+    gpu = MembraneModel(ode, None, 1, Space(X), verbose=False, devices=[0], scheme="dp45", rtol=1e-8, atol=1e-10)
+    load_tables(gpu, S, P)
+    lsoda, tight = (OracleMembraneModel(ode, None, 1, Space(X), oracle_name=name, n_sub=k) for k in (25, 800))
+    for m in (lsoda, tight):
+        m.states[:] = S
+        m.parameters[:] = P
+    stim = {"stim_amplitude": cfg["stim"]}
+    loc = lambda x: x[0] < 20e-6       # noqa: E731
+    for _ in range(3):
+        gpu.step_lsoda(cfg["dt"], stim, loc)
+        lsoda.step_lsoda_scipy(cfg["dt"], stim, loc)
+        tight.step_lsoda(cfg["dt"], stim, loc)
+    got = np.asarray(gpu.states)
+    gpu.close()
+    err_dev, err_lsoda = rel(got, tight.states), rel(lsoda.states, tight.states)
+    assert err_dev < 5e-7 and err_lsoda < 5e-7, (err_dev, err_lsoda)
+    assert rel(got, lsoda.states) < 5e-7
+    assert gpu.time == pytest.approx(lsoda.time)

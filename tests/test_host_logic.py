@@ -113,16 +113,17 @@ def test_fixed_step_scheme_warns_about_ignored_tolerances():
         MembraneModel(hh_test, None, 1, Space(np.zeros((4, 3))), verbose=False, exchange="lazy")
 
 
+@pytest.mark.parametrize("taper", [0, 1])
 @pytest.mark.parametrize("n", [0, 1, 1000, 65536, 300_000, 1_000_000, 10_000_000, 50_000_000, 123_456_789])
-def test_chunk_plan_covers_the_range_and_tapers(n):
-    """The DOF chunks of the pipelined exchange: contiguous, complete, non-increasing, and the
-    last chunk is small so that the pipeline's drain (one kernel + one copy) is short."""
+def test_chunk_plan_covers_the_range(n, taper):
+    """The DOF chunks of the pipelined exchange: contiguous, complete, non-increasing; equal
+    sixteenths by default, with a finely cut tail (a short pipeline drain) on request."""
     import ctypes as C
     from knpemi_b200 import _cabi
     off = (C.c_int64 * 128)()
     ln = (C.c_int64 * 128)()
     cnt = C.c_int(0)
-    _cabi.check(_cabi.lib().kem_plan_chunks(n, 16, off, ln, 128, C.byref(cnt)), "kem_plan_chunks")
+    _cabi.check(_cabi.lib().kem_plan_chunks(n, 16, taper, off, ln, 128, C.byref(cnt)), "kem_plan_chunks")
     k = cnt.value
     if n == 0:
         assert k == 0
@@ -133,4 +134,5 @@ def test_chunk_plan_covers_the_range_and_tapers(n):
     assert offs[-1] + lens[-1] == n and all(v > 0 for v in lens)
     assert all(lens[i] >= lens[i + 1] for i in range(k - 2))       # (the very last one is the remainder)
     if n >= 4_000_000:
-        assert lens[-1] <= 65536 and lens[0] >= n // 17 and max(lens) <= (n + 15) // 16 + 1024
+        assert lens[0] >= n // 17 and max(lens) <= (n + 15) // 16 + 1024
+        assert (lens[-1] <= 65536) if taper else (k == 16)
