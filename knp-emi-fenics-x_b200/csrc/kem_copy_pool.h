@@ -1,5 +1,6 @@
 // kem_copy_pool.h -- persistent worker threads for host-side staging copies.
 #pragma once
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -46,7 +47,7 @@ private:
 
     void run_parts(void *dst, const void *src, double value, size_t bytes)
     {
-        const size_t min_part = 1u << 20;
+        const size_t min_part = 512u << 10;
         int parts = (int)std::min<size_t>(workers_.size() + 1, (bytes + min_part - 1) / min_part);
         if (parts <= 1) {
             do_part((char *)dst, (const char *)src, value, bytes);
@@ -74,8 +75,14 @@ private:
 
     CopyPool()
     {
+        // every CPU this process may run on (a rank bound next to its GPU sees only those); the
+        // calling thread copies too.  One core moves 4-10 GB/s, the link 50.
         unsigned hw = std::thread::hardware_concurrency();
-        int n = (int)std::min<unsigned>(7u, hw > 2 ? hw / 2 - 1 : 0);
+#if defined(__linux__)
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0) hw = (unsigned)CPU_COUNT(&set);
+#endif
+        int n = (int)std::min<unsigned>(15u, hw > 1 ? hw - 1 : 0);
         if (const char *e = getenv("KNPEMI_COPY_THREADS")) n = std::max(0, atoi(e) - 1);
         for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
         for (auto &t : workers_) t.detach();

@@ -284,7 +284,7 @@ const KemModelDesc *model_desc(int id)
 constexpr int SMALL_RING = 8;
 constexpr size_t SMALL_BYTES = 64 * 1024;
 constexpr int N_STAGE = 3;
-constexpr size_t STAGE_BYTES = 8u << 20;
+constexpr size_t STAGE_BYTES = 16u << 20;
 constexpr int IO_MAX_CHUNKS = 96;
 constexpr int KEM_MAX_MAPS = 16;
 constexpr int IO_TARGET_CHUNKS = 16;   // measured best of 8/16/32/64 at 1e7 DOFs (profiles/r1_bench.md)

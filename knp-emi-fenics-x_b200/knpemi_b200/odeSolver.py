@@ -236,13 +236,19 @@ class MembraneModel:
         unread_inputs     what a full-column write to a parameter the right-hand side never
                           touches does: "auto" | "shadow" | "upload" | "discard"
                           (KEM_UNREAD_* of include/knpemi_b200.h).
-        exchange          "immediate" (default): every setter copies when it is called and
-                          `step_lsoda` returns after the kernel, like the reference.
-                          "deferred": setters of page-locked arrays only record the array (it must
-                          not be modified before the step), `step_lsoda` runs the whole exchange as
-                          one chunk-pipelined enqueue and returns at once, the first getter waits
-                          for the kernel chunk by chunk; a failed integration is reported by that
-                          getter (or :meth:`synchronize`) instead of `step_lsoda`.
+        exchange          "immediate" (default): every setter copies when it is called, every getter
+                          when it is called, and `step_lsoda` returns after the kernel, like the
+                          reference.
+                          "deferred": the caller promises what the reference's own loop does anyway
+                          (run_2D.py:88-109) -- arrays handed to a setter are not modified before
+                          `step_lsoda`, arrays a getter filled at the previous step are not read
+                          between `step_lsoda` and the same getter of this step.  Setters of
+                          page-locked arrays then only record the array; `step_lsoda` runs the
+                          whole exchange as one chunk-pipelined enqueue -- inputs in, kernel,
+                          outputs straight into the arrays the getters filled last time -- and
+                          returns at once; the getters wait for it (and copy normally if handed
+                          another array).  A failed integration is reported by the first getter
+                          (or :meth:`synchronize`) instead of `step_lsoda`.
         auto_register     page-lock caller arrays that come back a second time (see
                           :class:`_HostArrayCache`); no effect on results.
         """
@@ -318,6 +324,8 @@ class MembraneModel:
         self._mask_cache = {}          # id(locator) -> (locator, mask)
         self._registered = []          # host arrays page-locked by register_host_array
         self._pending = OrderedDict()  # exchange="deferred": (kind, col) -> (array, owner) not yet copied
+        self._bound_out = OrderedDict()  # ...: (kind, col) -> (array, owner) the getters filled last step
+        self._prefetched = {}          # ...: (kind, col) -> (ptr, nbytes) the running step writes itself
         self._status_pending = False   # an enqueue-only step whose status nobody has read yet
         self._stim_mask_key = "unset"
         self.last_step_times = None
@@ -330,7 +338,7 @@ class MembraneModel:
         h, self._h = getattr(self, "_h", None), None
         if h:
             self._lib.kem_destroy(h)                   # waits for the handle's streams
-        self._pending = OrderedDict()
+        self._pending, self._bound_out, self._prefetched = OrderedDict(), OrderedDict(), {}
         self._inflight = None
         for a in getattr(self, "_registered", []):
             self._lib.kem_host_unregister(a.ctypes.data)
@@ -420,16 +428,25 @@ class MembraneModel:
         return self.states
 
     def _step_deferred(self, dt, n_sub, cols, vals, n_stim):
-        '''exchange="deferred": the recorded setter arrays go in, the step runs, all as one
-        chunk-pipelined enqueue (H2D of chunk c+1 under the kernel of chunk c); nothing waits.'''
+        '''exchange="deferred": the recorded setter arrays go in, the step runs, the columns the
+        getters asked for last time come back into the same arrays -- one chunk-pipelined
+        enqueue (H2D of chunk c+1 under the kernel of chunk c under D2H of chunk c-1); nothing waits.'''
         pend, self._pending = self._pending, OrderedDict()
-        if pend:
-            arr = (kem_io_column * len(pend))()
+        bound, self._bound_out = self._bound_out, OrderedDict()
+        self._prefetched = {}
+        if pend or bound:
+            a_in = (kem_io_column * max(len(pend), 1))()
             for k, ((kind, col), (a, _owner)) in enumerate(pend.items()):
-                arr[k].kind, arr[k].col, arr[k].host = kind, col, a.ctypes.data
-            self._inflight = pend                  # keep the arrays alive until the copies are done
+                a_in[k].kind, a_in[k].col, a_in[k].host = kind, col, a.ctypes.data
+            a_out = (kem_io_column * max(len(bound), 1))()
+            for k, ((kind, col), (a, _owner)) in enumerate(bound.items()):
+                a_out[k].kind, a_out[k].col, a_out[k].host = kind, col, a.ctypes.data
+                self._prefetched[(kind, col)] = (a.ctypes.data, a.nbytes)
+            self._inflight = (pend, bound)         # keep the arrays alive until the copies are done
             rc = self._lib.kem_step_io(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
-                                       n_stim, cols, vals, len(pend), arr, 0, None, None, None)
+                                       n_stim, cols, vals, len(pend), a_in, len(bound), a_out, None, None)
+            if rc != 0:
+                self._prefetched = {}
             check(rc, "kem_step_io")
         else:
             check(self._lib.kem_step(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
@@ -461,6 +478,13 @@ class MembraneModel:
             pend, self._pending = self._pending, OrderedDict()
             for (kind, col), (a, _owner) in pend.items():
                 self._set_column(kind, col, a[:self.nodes])
+
+    def _wait_exchange(self):
+        '''Wait for the enqueue-only exchange (its outputs are in the caller's arrays afterwards).'''
+        if self._status_pending:
+            self._settle()
+        else:
+            check(self._lib.kem_sync(self._h), "kem_sync")
 
     def _settle(self):
         '''After a getter has waited for the device: report the status of an enqueue-only step.'''
@@ -761,6 +785,7 @@ class MembraneModel:
 
     def _set_column(self, kind, col, src):
         self._pending.pop((kind, col), None)            # a recorded write to this column is superseded
+        self._prefetched.pop((kind, col), None)         # ... and what the step wrote back is stale
         check(self._lib.kem_set_column(self._h, kind, col, src.ctypes.data, self.nodes), "kem_set_column")
 
     def _get_column(self, kind, col, dst):
@@ -784,6 +809,7 @@ class MembraneModel:
             if self.exchange == "deferred" and (pinned or _cabi.host_is_pinned(source)):
                 # only recorded: copied by the next step, pipelined with the kernel
                 self._pending.pop((kind, col), None)
+                self._prefetched.pop((kind, col), None)
                 self._pending[(kind, col)] = (source, u)
             else:
                 self._set_column(kind, col, source)
@@ -805,8 +831,15 @@ class MembraneModel:
                   and dest.ndim == 1 and dest.flags.c_contiguous and dest.flags.writeable
                   and len(dest) >= self.nodes)
         if direct:
-            if self.auto_register:
-                _HOST_CACHE.sight(u, dest)
+            pinned = self.auto_register and _HOST_CACHE.sight(u, dest)
+            if self.exchange == "deferred":
+                if self._prefetched.pop((kind, col), None) == (dest.ctypes.data, dest.nbytes) and not self._pending:
+                    # the running step is writing this column into this very array: wait for it
+                    self._bound_out[(kind, col)] = (dest, u)
+                    self._wait_exchange()
+                    return u
+                if pinned or _cabi.host_is_pinned(dest):
+                    self._bound_out[(kind, col)] = (dest, u)    # the next step writes it back itself
             self._get_column(kind, col, dest)
             return u
         tmp = np.empty(self.nodes, dtype=np.float64)

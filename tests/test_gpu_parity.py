@@ -20,13 +20,21 @@ def rel_err(got, want, floor):
     return float(np.max(np.abs(got - want) / np.maximum(np.abs(want), floor)))
 
 
-def scales(want):
-    """Per-column magnitude floor.  A channel current is a difference of O(column max)
-    terms (i_Kir - 2 i_pump, ...), so at a DOF where it crosses zero its last-bit noise
-    (~1e-14 absolute, measured with both math builds) is not small *relative to the
-    entry*.  Errors are therefore measured against max(|entry|, 1e-3 * column max):
-    1e-10 relative everywhere, with an absolute floor of 1e-13 * column scale."""
-    return np.maximum(1e-3 * np.max(np.abs(want), axis=0, keepdims=True), 1e-300)
+STATE_FLOOR, CURRENT_FLOOR = 1e-6, 3e-4
+
+
+def scales(want, frac=CURRENT_FLOOR):
+    """Per-column magnitude floor: errors are measured against max(|entry|, frac * column max).
+
+    States are compared with frac = 1e-6: in every workload here they pass 1e-10 strictly, per
+    entry (tests/diag_parity.py, profiles/r2_parity_strict.md: worst 6.6e-11); the floor only
+    guards a state that crosses zero.  A channel current is g (V - E) + pump terms: its error is
+    the state error times the conductance, 1e-14 .. 2e-13 of the column's scale at EVERY DOF,
+    also where the terms cancel and the current itself is 1e-5 of that scale.  1 to 4 entries in
+    20 000 sit there; they need a floor of up to 9.5e-5 of the column maximum -- with the triage
+    build (CUDA libm, IEEE division) as well: conditioning of the quantity, not error of the
+    kernel.  Currents and whole parameter tables are therefore compared with frac = 3e-4."""
+    return np.maximum(frac * np.max(np.abs(want), axis=0, keepdims=True), 1e-300)
 
 
 def run_pair(name, n, n_steps, math="fast", devices=(0,), n_sub=25, seed=20240611, block=0):
@@ -60,7 +68,7 @@ def run_pair(name, n, n_steps, math="fast", devices=(0,), n_sub=25, seed=2024061
 def test_kernel_matches_oracle(built, name):
     """20 000 DOFs x 10 PDE steps with a masked sticky stimulus, all six models."""
     got_S, got_P, S, P = run_pair(name, 20000, 10)
-    assert rel_err(got_S, S, scales(S)) < RTOL
+    assert rel_err(got_S, S, scales(S, STATE_FLOOR)) < RTOL
     # every parameter column, including the I_ch_* outputs and the sticky stimulus column
     assert rel_err(got_P, P, scales(P)) < RTOL
 
@@ -71,8 +79,8 @@ def test_libm_build_matches_oracle_tightly(built, name):
     FMA contraction and libm last-bit differences: states two orders tighter than RTOL
     (the currents carry the cancellation noise described in `scales`)."""
     got_S, got_P, S, P = run_pair(name, 5000, 10, math="libm")
-    assert rel_err(got_S, S, scales(S)) < 1e-12
-    assert rel_err(got_P, P, scales(P)) < 5e-11
+    assert rel_err(got_S, S, scales(S, 1e-3)) < 1e-12       # (1e-12 is an absolute-error statement:
+    assert rel_err(got_P, P, scales(P, 1e-3)) < 5e-11       #  the scale of round 1 is kept for it)
 
 
 @pytest.mark.parametrize("name", MODELS)
@@ -91,7 +99,7 @@ def test_golden_trajectories(built, name):
         model.step_lsoda(dt=float(g["dt"]), stimulus=None)
     got_S, got_P = np.asarray(model.states), np.asarray(model.parameters)
     model.close()
-    assert rel_err(got_S, g["states"], scales(g["states"])) < RTOL
+    assert rel_err(got_S, g["states"], scales(g["states"], STATE_FLOOR)) < RTOL
     assert rel_err(got_P, g["params"], scales(g["params"])) < RTOL
 
 
@@ -99,7 +107,7 @@ def test_config2_hh_test_1e6(built):
     """BASELINE config #2: tests/mm_test_ode.py HH system on 10^6 synthetic DOFs, inputs
     bit-identical between oracle and kernel, 1e-10 on all 4 states and 3 currents."""
     got_S, got_P, S, P = run_pair("hh_test", 1_000_000, 5)
-    assert rel_err(got_S, S, scales(S)) < RTOL
+    assert rel_err(got_S, S, scales(S, STATE_FLOOR)) < RTOL
     assert rel_err(got_P[:, 8:11], P[:, 8:11], scales(P[:, 8:11])) < RTOL
 
 
@@ -148,7 +156,7 @@ def test_removable_singularity_of_the_rate_functions(built):
     load_tables(m, S, P)
     m.step_lsoda(1e-3, None)                    # one RK4 step of 1 us: the states stay next to -40 mV
     assert cpu_oracle.step(name, S, P, 0.0, 1e-3, 1) == 0
-    assert rel_err(np.asarray(m.states), S, scales(S)) < RTOL
+    assert rel_err(np.asarray(m.states), S, scales(S, STATE_FLOOR)) < RTOL
     m.close()
     # exactly on the singularity: 0/0 -> NaN on both sides
     S1 = np.tile(ode.init_state_values(), (1, 1))
@@ -159,3 +167,27 @@ def test_removable_singularity_of_the_rate_functions(built):
         m.step_lsoda(0.1, None)
     assert cpu_oracle.step(name, S1, P[:1].copy(), 0.0, 0.1, 25) == 1
     m.close()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_strict_per_entry_parity_report(built, name):
+    """north_star: 1e-10 relative on all states and I_ch.  Strictly per entry, without any
+    floor: every state entry passes; of the current entries at most a handful in 20 000 do
+    not -- the ones where the current's terms cancel -- and the floor they need stays below the
+    one the tests use, for the product build and for the libm build alike."""
+    import json
+    import os
+    from diag_parity import parity_report
+    rep = parity_report(name, 20000, 10)
+    for math, cols in rep["builds"].items():
+        for col, e in cols.items():
+            if col.startswith("state"):
+                assert e["n_above_tol"] == 0 and e["strict_max_rel"] < RTOL, (math, col, e)
+            else:
+                assert e["n_above_tol"] <= 8, (math, col, e)
+                assert e["min_floor_frac"] < CURRENT_FLOOR / 2, (math, col, e)
+                assert e["abs_over_colmax"] < 1e-12, (math, col, e)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, f"parity_strict_{name}.json"), "w") as f:
+            json.dump(rep, f, indent=1)
