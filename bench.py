@@ -425,14 +425,16 @@ class Part:
         got_c = np.asarray(m.parameters)[:, out_cols] if out_cols else np.zeros((len(idx), 0))
         m.close()
 
-        def rel(a, b):
+        def rel(a, b, floor):
             if b.size == 0:
                 return 0.0
-            scale = np.maximum(np.abs(b), 1e-6 * np.max(np.abs(b), axis=0, keepdims=True) + 1e-300)
+            scale = np.maximum(np.abs(b), floor * np.max(np.abs(b), axis=0, keepdims=True) + 1e-300)
             return float(np.max(np.abs(a - b) / scale))
-        return {"rows": int(len(idx)), "pde_steps": steps, "max_rel_err_states": rel(got_s, S),
-                "max_rel_err_currents": rel(got_c, P[:, out_cols]), "tolerance": 1e-10,
-                "floor": "1e-6 x column max"}
+        # the floors of tests/test_gpu_parity.py (states 1e-6, currents 3e-4 of the column maximum;
+        # profiles/r2_parity_strict.md says why a current needs one)
+        return {"rows": int(len(idx)), "pde_steps": steps, "max_rel_err_states": rel(got_s, S, 1e-6),
+                "max_rel_err_currents": rel(got_c, P[:, out_cols], 3e-4), "tolerance": 1e-10,
+                "floor": "states 1e-6, currents 3e-4 x column max"}
 
 
 def measure_link(dev, dist, copy_bytes, reps_h2d, reps_d2h):

@@ -294,7 +294,7 @@ struct Shard {
     int dev = 0;
     int64_t begin = 0, n = 0;
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
-    cudaStream_t s_in2 = nullptr;     // optional second host->device stream (KNPEMI_IO_H2D_STREAMS=2)
+    cudaStream_t s_in2 = nullptr;     // second host->device stream of kem_step_io
     cudaStream_t stream2 = nullptr;   // second compute stream: chunk kernels of kem_step_io alternate
                                       // between the two so one chunk's tail overlaps the next one's head
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
@@ -1707,8 +1707,10 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
         CK(cudaStreamWaitEvent(s.stream2, s.ev_a, 0));
         CK(cudaStreamWaitEvent(s.s_out, s.ev_a, 0));
         CK(cudaEventRecord(s.ev_b, s.s_in));   // t = 0 of this shard's exchange
-        // (experiment knob: spread the input columns over two copy streams)
-        static const bool two_in = getenv("KNPEMI_IO_H2D_STREAMS") && atoi(getenv("KNPEMI_IO_H2D_STREAMS")) == 2;
+        // the input columns alternate over two copy streams: more read requests in flight while
+        // the device->host writes share the link (measured -4 % per exchange, profiles/r2_exchange.md;
+        // KNPEMI_IO_H2D_STREAMS=1 puts them back on one)
+        static const bool two_in = !(getenv("KNPEMI_IO_H2D_STREAMS") && atoi(getenv("KNPEMI_IO_H2D_STREAMS")) == 1);
         if (two_in) CK(cudaStreamWaitEvent(s.s_in2, s.ev_a, 0));
         for (size_t c = 0; c < n_chunks; ++c) {
             for (int k = 0; k < n_in; ++k)
