@@ -165,6 +165,10 @@ int kem_sync(kem_handle h);
  * compute streams) instead of one grid: a kem_get_column into page-locked memory that
  * follows then copies chunk c while chunk c+1 still computes.  1 (default) = one launch. */
 int kem_set_step_chunks(kem_handle h, int n_chunks);
+/* Tuning of kem_step_io's pipeline for this handle: DOF chunks per device (0 = default 16 /
+ * KNPEMI_IO_CHUNKS) and host->device copy streams the input columns alternate over (0 = default
+ * 2 / KNPEMI_IO_H2D_STREAMS, 1, 2).  Results do not depend on either. */
+int kem_set_io_tuning(kem_handle h, int n_chunks, int h2d_streams);
 /* The DOF chunks kem_step_io / a chunked kem_step cut a range of n DOFs into (offsets and
  * lengths, at most `cap` written, the count always returned): `target` equal chunks; with
  * taper = 1 the tail is halved repeatedly so that the pipeline drains through a small last

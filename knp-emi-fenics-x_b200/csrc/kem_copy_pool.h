@@ -82,6 +82,11 @@ private:
         cpu_set_t set;
         if (sched_getaffinity(0, sizeof set, &set) == 0) hw = (unsigned)CPU_COUNT(&set);
 #endif
+        // several ranks on one host (torchrun sets LOCAL_WORLD_SIZE) share those CPUs
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) {
+            const unsigned ranks = (unsigned)std::max(1, atoi(e));
+            hw = std::max(1u, hw / ranks);
+        }
         int n = (int)std::min<unsigned>(15u, hw > 1 ? hw - 1 : 0);
         if (const char *e = getenv("KNPEMI_COPY_THREADS")) n = std::max(0, atoi(e) - 1);
         for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });

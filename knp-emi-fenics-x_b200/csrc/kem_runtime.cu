@@ -287,7 +287,10 @@ constexpr int N_STAGE = 3;
 constexpr size_t STAGE_BYTES = 16u << 20;
 constexpr int IO_MAX_CHUNKS = 96;
 constexpr int KEM_MAX_MAPS = 16;
-constexpr int IO_TARGET_CHUNKS = 16;   // measured best of 8/16/32/64 at 1e7 DOFs (profiles/r1_bench.md)
+const int IO_TARGET_CHUNKS = [] {       // 16: measured best of 8/16/32/64 at 1e7 DOFs (profiles/r1_bench.md)
+    const char *e = getenv("KNPEMI_IO_CHUNKS");
+    return e && atoi(e) > 0 ? atoi(e) : 16;
+}();
 constexpr int64_t IO_MIN_CHUNK = 1 << 16;   // smallest tail chunk of the pipeline (0.5 MB per column)
 
 struct Shard {
@@ -353,6 +356,8 @@ struct kem_handle_s {
     bool shadow_pinned_io = true;     // KEM_UNREAD_AUTO: pinned inputs of kem_step_io to dead slots are shadowed
     std::vector<char> out_const_valid;   // per constant output slot: 1 = the column holds the literal
     int step_chunks = 1;              // kem_step: launch the range as this many chunks (getter overlap)
+    int io_chunks = 0;                // kem_step_io: chunks per shard (0 = IO_TARGET_CHUNKS / KNPEMI_IO_CHUNKS)
+    int io_h2d_streams = 0;           // kem_step_io: 1 or 2 host->device streams (0 = default / KNPEMI_IO_H2D_STREAMS)
     bool uni_dirty = true;
     int block = 0;
     int64_t launches = 0;
@@ -642,7 +647,6 @@ void plan_chunks(int64_t n, int target, std::vector<int64_t> &off, std::vector<i
     off.clear();
     len.clear();
     if (n <= 0) return;
-    if (const char *e = getenv("KNPEMI_IO_CHUNKS")) target = atoi(e);
     target = std::max(1, std::min(target, IO_MAX_CHUNKS / 2));
     int64_t chunk = std::max<int64_t>((n + target - 1) / target, 2 * IO_MIN_CHUNK);
     chunk = (chunk + 1023) / 1024 * 1024;
@@ -1697,7 +1701,7 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
     for (Shard &s : h->shards) {
         if (s.n == 0) continue;
         CK(cudaSetDevice(s.dev));
-        plan_chunks(s.n, IO_TARGET_CHUNKS, s.ch_off, s.ch_len);
+        plan_chunks(s.n, h->io_chunks > 0 ? h->io_chunks : IO_TARGET_CHUNKS, s.ch_off, s.ch_len);
         const size_t n_chunks = s.ch_off.size();
         rc = ensure_chunk_events(s, n_chunks);
         if (rc) return rc;
@@ -1710,7 +1714,8 @@ int kem_step_io(kem_handle h, double t0, double dt, int n_sub, int scheme, int n
         // the input columns alternate over two copy streams: more read requests in flight while
         // the device->host writes share the link (measured -4 % per exchange, profiles/r2_exchange.md;
         // KNPEMI_IO_H2D_STREAMS=1 puts them back on one)
-        static const bool two_in = !(getenv("KNPEMI_IO_H2D_STREAMS") && atoi(getenv("KNPEMI_IO_H2D_STREAMS")) == 1);
+        static const bool two_in_env = !(getenv("KNPEMI_IO_H2D_STREAMS") && atoi(getenv("KNPEMI_IO_H2D_STREAMS")) == 1);
+        const bool two_in = h->io_h2d_streams ? h->io_h2d_streams == 2 : two_in_env;
         if (two_in) CK(cudaStreamWaitEvent(s.s_in2, s.ev_a, 0));
         for (size_t c = 0; c < n_chunks; ++c) {
             for (int k = 0; k < n_in; ++k)
@@ -1801,6 +1806,16 @@ int kem_plan_chunks(int64_t n, int target, int taper, int64_t *off_out, int64_t 
         if (off_out) off_out[k] = off[k];
         if (len_out) len_out[k] = len[k];
     }
+    return KEM_OK;
+}
+
+int kem_set_io_tuning(kem_handle h, int n_chunks, int h2d_streams)
+{
+    ARG(h, "null handle");
+    ARG(n_chunks >= 0 && n_chunks <= IO_MAX_CHUNKS / 2, "n_chunks out of range");
+    ARG(h2d_streams >= 0 && h2d_streams <= 2, "h2d_streams must be 0 (default), 1 or 2");
+    h->io_chunks = n_chunks;
+    h->io_h2d_streams = h2d_streams;
     return KEM_OK;
 }
 

@@ -88,6 +88,7 @@ SIGNATURES = {
     "kem_sync": (C.c_int, [_H]),
     "kem_set_unread_policy": (C.c_int, [_H, C.c_int]),
     "kem_set_step_chunks": (C.c_int, [_H, C.c_int]),
+    "kem_set_io_tuning": (C.c_int, [_H, C.c_int, C.c_int]),
     "kem_plan_chunks": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                   C.c_int, _IP]),
     "kem_set_tolerances": (C.c_int, [_H, C.c_double, C.c_double]),
