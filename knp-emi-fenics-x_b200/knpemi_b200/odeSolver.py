@@ -624,12 +624,16 @@ class MembraneModel:
         return arr
 
     def shard_ranges(self):
-        '''[(device, begin, end)] of the contiguous DOF ranges of this model's devices.'''
+        '''[(device, begin, end)] of the contiguous DOF ranges of this model's devices (the rule
+        of knpemi_b200.sharding.dof_ranges, as applied by kem_create).'''
+        from .sharding import dof_ranges
         out = []
         for k in range(len(self.devices)):
             dev, b, e = C.c_int(), C.c_int64(), C.c_int64()
             check(self._lib.kem_shard_range(self._h, k, C.byref(dev), C.byref(b), C.byref(e)), "kem_shard_range")
             out.append((dev.value, b.value, e.value))
+        if [(b, e) for _, b, e in out] != dof_ranges(self.nodes, len(self.devices)):
+            raise KemError("library and host disagree about the DOF ranges of the devices")
         return out
 
     # ------------------------------------------------------------------ helpers
