@@ -624,7 +624,7 @@ def run_gpu(args, dist: Dist):
     dropin = {}
     p0 = parts[0]
     in_names, v_io, out_names = IO_COLUMNS[p0.name]
-    if v_io and in_names and len(parts) == 1 and not args.no_dropin:
+    if v_io and in_names and len(parts) == 1 and dist.world == 1 and not args.no_dropin:      # like cpu_baseline: N = 1 only
         from knpemi_b200.ducks import PointSpace
         from knpemi_b200.odeSolver import MembraneModel
         from workloads import load_tables

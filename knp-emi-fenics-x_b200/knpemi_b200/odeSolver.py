@@ -116,6 +116,18 @@ class _HostArrayCache:
 _HOST_CACHE = _HostArrayCache()
 
 
+def _release_host_cache_at_exit():
+    try:
+        _HOST_CACHE.release_all()          # unpin before the interpreter frees the arrays
+    except Exception:
+        pass
+
+
+import atexit as _atexit  # noqa: E402
+
+_atexit.register(_release_host_cache_at_exit)
+
+
 def _default_devices():
     env = os.environ.get("KNPEMI_B200_DEVICES")
     if env:
