@@ -739,18 +739,37 @@ class MembraneModel:
             # answers the same on a sample of rows: a locator that closes over something the
             # caller changes (a moving stimulus region) is re-evaluated, not served stale.
             # `strict_locators=True` re-evaluates every row every time.
-            cached = hit[1]
-            rows = self._sample_rows(self.nodes)
-            X = self.dof_locations
-            if all(bool(locator(X[k])) == (True if cached is None else bool(cached[k])) for k in rows):
-                return cached
-        mask = self._rows_of(locator)
+            if self._same_on_sample(locator, hit[1], hit[2]):
+                return hit[1]
+        mask, vectorised = self._rows_of(locator, tell=True)
         if mask.all():
             mask = None        # every row selected: same as no locator
         if len(self._mask_cache) >= _MASK_CACHE_ENTRIES:     # a caller that builds a new lambda
             self._mask_cache.pop(next(iter(self._mask_cache)))   # per step must not pile up masks
-        self._mask_cache[id(locator)] = (locator, mask)
+        self._mask_cache[id(locator)] = (locator, mask, vectorised)
         return mask
+
+    def _sample(self):
+        '''(rows, their coordinates, the same transposed): the rows a vectorised evaluation is
+        checked on; computed once per model.'''
+        smp = getattr(self, "_sample_rows_cache", None)
+        if smp is None or smp[3] != self.nodes:
+            rows = self._sample_rows(self.nodes)
+            Xs = np.ascontiguousarray(self.dof_locations[rows])
+            smp = self._sample_rows_cache = (rows, Xs, np.ascontiguousarray(Xs.T), self.nodes)
+        return smp
+
+    def _same_on_sample(self, locator, cached, vectorised):
+        rows, Xs, XsT, _ = self._sample()
+        want = np.ones(len(rows), dtype=bool) if cached is None else cached[rows]
+        if vectorised:                      # one call on the [gdim, k] sample instead of k calls
+            try:
+                r = np.asarray(locator(XsT))
+                if r.shape == want.shape and r.dtype == np.bool_:
+                    return bool(np.array_equal(r, want))
+            except Exception:
+                pass
+        return all(bool(locator(Xs[k])) == bool(want[k]) for k in range(len(rows)))
 
     def _sample_rows(self, n):
         if n <= _SAMPLE_ROWS:
@@ -758,19 +777,22 @@ class MembraneModel:
         rng = np.random.default_rng(n)
         return np.unique(np.concatenate(([0, n - 1], rng.integers(0, n, _SAMPLE_ROWS - 2))))
 
-    def _rows_of(self, locator):
+    def _rows_of(self, locator, tell=False):
+        '''Row mask of a locator; with `tell` also whether the vectorised evaluation gave it.'''
         X = self.dof_locations
         n = len(X)
         if not self.strict_locators and n > _SAMPLE_ROWS:
             try:
                 r = np.asarray(locator(X.T))
                 if r.shape == (n,) and r.dtype == np.bool_:
-                    rows = self._sample_rows(n)
-                    if all(bool(locator(X[k])) == bool(r[k]) for k in rows):
-                        return np.ascontiguousarray(r)
+                    rows, Xs, _, _ = self._sample()
+                    if all(bool(locator(Xs[k])) == bool(r[rows[k]]) for k in range(len(rows))):
+                        mask = np.ascontiguousarray(r)
+                        return (mask, True) if tell else mask
             except Exception:
                 pass
-        return np.fromiter(map(locator, X), dtype=bool, count=n)       # the reference's path
+        mask = np.fromiter(map(locator, X), dtype=bool, count=n)       # the reference's path
+        return (mask, False) if tell else mask
 
     def _values_of(self, get_value, rows):
         '''float64 array of get_value(x) for the selected rows (odeSolver.py:183-187).'''
@@ -786,7 +808,7 @@ class MembraneModel:
                 else:
                     cand = np.asarray(r, dtype=np.float64)
                 if cand.shape == (n,):
-                    rows_s = self._sample_rows(n)
+                    rows_s = self._sample_rows(n) if rows is not None else self._sample()[0]
                     ok = True
                     for k in rows_s:
                         v = float(get_value(X[k]))

@@ -162,3 +162,34 @@ def test_device_dp45_against_lsoda_at_the_reference_tolerances(built, name):
     assert err_dev < 5e-7 and err_lsoda < 5e-7, (err_dev, err_lsoda)
     assert rel(got, lsoda.states) < 5e-7
     assert gpu.time == pytest.approx(lsoda.time)
+
+
+@pytest.mark.parametrize("name", ["hh_tissue", "hh_ideal", "calibration"])
+def test_device_rk4_at_lsoda_accuracy_level(built, name):
+    """Row A3 on the device: the product's default scheme O1 (RK4 x 25, the CUDA kernel) against
+    LSODA at the reference's tolerances and against a tight solution, like
+    tests/test_oracle_lsoda.py does for the CPU restatement.  The integrator the reference uses
+    (numbalsoda, absent and un-pinned) cannot be pinned; this bounds the difference: the
+    fixed-step scheme sits at the accuracy level of the integrator it replaces."""
+    from knpemi_b200.odeSolver import MembraneModel
+    from oracle.membrane_oracle import OracleMembraneModel
+    n = 8
+    ode = builtin(name)
+    cfg = SETUP[name]
+    S, P, X, mask = synthetic_tables(name, n, seed=3)
+    gpu = MembraneModel(ode, None, 1, Space(X), verbose=False, devices=[0], n_sub=25)
+    load_tables(gpu, S, P)
+    lsoda, tight = (OracleMembraneModel(ode, None, 1, Space(X), oracle_name=name, n_sub=k) for k in (25, 800))
+    for m in (lsoda, tight):
+        m.states[:] = S
+        m.parameters[:] = P
+    stim = {"stim_amplitude": cfg["stim"]}
+    loc = lambda x: x[0] < 20e-6       # noqa: E731
+    for _ in range(3):
+        gpu.step_lsoda(cfg["dt"], stim, loc)
+        lsoda.step_lsoda_scipy(cfg["dt"], stim, loc)
+        tight.step_lsoda(cfg["dt"], stim, loc)
+    got = np.asarray(gpu.states)
+    gpu.close()
+    assert rel(got, tight.states) < 5e-7 and rel(lsoda.states, tight.states) < 5e-7
+    assert rel(got, lsoda.states) < 5e-7

@@ -384,3 +384,36 @@ def test_every_device_of_the_box_in_one_handle(built):
     assert np.array_equal(np.asarray(one.parameters), np.asarray(many.parameters))
     one.close()
     many.close()
+
+
+def test_pipeline_tuning_does_not_change_results(built):
+    """kem_set_io_tuning (chunks per device, copy streams) and the taper only reshape the
+    pipeline: every setting gives the same bits."""
+    import ctypes as C
+    from knpemi_b200._cabi import check
+    name, n = "hh_ideal", 1_500_003
+    ode = builtin(name)
+    ref = None
+    for chunks, streams in ((0, 0), (1, 1), (4, 2), (32, 1), (48, 2)):
+        m, S, P, X = _model(name, n)
+        check(m._lib.kem_set_io_tuning(m._h, chunks, streams), "kem_set_io_tuning")
+        rng = np.random.default_rng(2)
+        ins = {("parameter", k): _pinned(P[:, ode.parameter_indices(k)] * (1 + 0.01 * rng.uniform(-1, 1, n)))
+               for k in IONS_IN}
+        ins[("state", "V")] = _pinned(S[:, 3])
+        outs = {("state", "V"): _pinned(np.zeros(n)), **{("parameter", k): _pinned(np.ones(n)) for k in IONS_OUT}}
+        for _ in range(2):
+            m.step_exchange(1e-4, ins, outs, {"stim_amplitude": 10.0}, lambda x: x[0] < 20e-6)
+        got = {k: np.array(v) for k, v in outs.items()}
+        got["states"] = np.asarray(m.states)
+        m.close()
+        if ref is None:
+            ref = got
+        else:
+            for k in ref:
+                assert np.array_equal(ref[k], got[k]), (chunks, streams, k)
+    cnt = C.c_int(0)
+    from knpemi_b200 import _cabi
+    assert _cabi.lib().kem_set_io_tuning(None, 0, 0) < 0            # null handle is an argument error
+    _cabi.check(_cabi.lib().kem_plan_chunks(n, 48, 0, None, None, 0, C.byref(cnt)), "kem_plan_chunks")
+    assert cnt.value == 48
