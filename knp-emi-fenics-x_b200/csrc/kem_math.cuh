@@ -183,6 +183,7 @@ KEM_HD double div(double a, double b)
 __constant__ double KEM_EXP_C_DEV[6] = KEM_EXP_CONSTS;
 __device__ const double KEM_EXP_T_DEV[KEM_EXP_TABLE_SIZE] = {KEM_EXP_TABLE_VALUES};
 __shared__ double kem_exp_tab_s[KEM_EXP_TABLE_SIZE];
+__constant__ uint32_t KEM_EXP_BIAS_DEV = 0x3ff00000u;
 #endif
 static const double KEM_EXP_C_HOST[6] = KEM_EXP_CONSTS;
 static const double KEM_EXP_T_HOST[KEM_EXP_TABLE_SIZE] = {KEM_EXP_TABLE_VALUES};
@@ -241,7 +242,14 @@ KEM_HD double exp(double x)
     m = m < -1023 * 256 ? -1023 * 256 : (m > 1024 * 256 ? 1024 * 256 : m);
     const double T = KEM_EXP_T[m & (KEM_EXP_TABLE_SIZE - 1)];
     // high word of 2^k: (k + 1023) << 20 = (256 k) * 4096 + (1023 << 20)
+#if defined(__CUDA_ARCH__)
+    // (one IMAD: the bias comes from constant memory so that ptxas cannot fold it into a
+    // separate add before the shift)
+    uint32_t hi;
+    asm("mad.lo.u32 %0, %1, 4096, %2;" : "=r"(hi) : "r"((uint32_t)(m & ~(KEM_EXP_TABLE_SIZE - 1))), "r"(KEM_EXP_BIAS_DEV));
+#else
     const uint32_t hi = (uint32_t)(m & ~(KEM_EXP_TABLE_SIZE - 1)) * 4096u + 0x3ff00000u;
+#endif
     const double scale = bits_to_double((uint64_t)hi << 32);
     double q = fma(KEM_EXP_C[4], r, KEM_EXP_C[5]);
     q = fma(q, r, 0.5);
