@@ -136,3 +136,76 @@ def test_chunk_plan_covers_the_range(n, taper):
     if n >= 4_000_000:
         assert lens[0] >= n // 17 and max(lens) <= (n + 15) // 16 + 1024
         assert (lens[-1] <= 65536) if taper else (k == 16)
+
+
+class _FakeLib:
+    """Stands in for libknpemi_b200 in the host-array cache tests (no device here)."""
+
+    def __init__(self, refuse=()):
+        self.registered, self.refuse, self.log = {}, set(refuse), []
+
+    def kem_host_register(self, ptr, nbytes):
+        p = ptr.value
+        if p in self.refuse:
+            return -1
+        self.registered[p] = self.registered.get(p, 0) + 1
+        self.log.append(("reg", p))
+        return 0
+
+    def kem_host_unregister(self, ptr):
+        p = ptr.value
+        self.registered[p] -= 1
+        if not self.registered[p]:
+            del self.registered[p]
+        self.log.append(("unreg", p))
+        return 0
+
+    def kem_last_error(self):
+        return b"refused"
+
+
+def test_host_array_cache_registers_on_the_second_sighting_of_a_living_owner(monkeypatch):
+    """What the reference's callers hand over (utils.py:137-142, 190-191; run_2D.py:105-109):
+    persistent getter targets are page-locked the second time they arrive, single-use trace
+    Functions never are -- not even when a new array lands on a recycled address."""
+    import gc
+    from ducks_for_tests import Func
+    from knpemi_b200 import _cabi, odeSolver
+    fake = _FakeLib()
+    monkeypatch.setattr(_cabi, "lib", lambda: fake)
+    cache = odeSolver._HostArrayCache(max_pinned=2, min_bytes=1024)
+    keep = Func(np.zeros(4096))
+    assert cache.sight(keep, keep.x.array) is False            # first sighting: only noted
+    assert cache.sight(keep, keep.x.array) is True             # second: registered
+    assert cache.sight(keep, keep.x.array) is True and len(fake.log) == 1
+    # too small, wrong dtype, non-contiguous: never
+    assert cache.sight(keep, np.zeros(8)) is False
+    assert cache.sight(keep, np.zeros(4096, dtype=np.float32)) is False
+    assert cache.sight(keep, np.zeros(8192)[::2]) is False
+    # a fresh owner per step at (possibly) the same address is a first sighting every time
+    for _ in range(5):
+        fresh = Func(np.zeros(4096))
+        assert cache.sight(fresh, fresh.x.array) is False
+        del fresh
+        gc.collect()
+    assert len(fake.registered) == 1
+    # same memory offered by ANOTHER owner object is not the second sighting of the first
+    a = np.zeros(4096)
+    u1, u2 = Func(np.zeros(1)), Func(np.zeros(1))
+    u1.x.array = a
+    u2.x.array = a
+    assert cache.sight(u1, a) is False and cache.sight(u2, a) is False and cache.sight(u2, a) is True
+    # least-recently-used eviction unregisters
+    third = Func(np.zeros(4096))
+    cache.sight(third, third.x.array)
+    assert cache.sight(third, third.x.array) is True
+    assert len(cache.pinned) == 2 and ("unreg", keep.x.array.ctypes.data) in fake.log
+    # a range the library refuses is remembered, not retried every step
+    bad = Func(np.zeros(4096))
+    fake.refuse.add(bad.x.array.ctypes.data)
+    cache.sight(bad, bad.x.array)
+    n_calls = len(fake.log)
+    assert cache.sight(bad, bad.x.array) is False and cache.sight(bad, bad.x.array) is False
+    assert len(fake.log) == n_calls
+    cache.release_all()
+    assert not fake.registered and not cache.pinned
