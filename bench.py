@@ -312,7 +312,8 @@ def run_reference(args, dist: Dist):
         return
     from workloads import SETUP
     parts, cfg_text, strong = workload_parts(args.workload)
-    value, threads, sample, s_per_step = cpu_port_rate(args.workload, args.steps, max(args.warmup, 1), 150.0)
+    budget_s = float(os.environ.get("KNPEMI_BENCH_REF_BUDGET_S", "150"))      # whole run within ~2.5 min
+    value, threads, sample, s_per_step = cpu_port_rate(args.workload, args.steps, max(args.warmup, 1), budget_s)
     head = parts[0][0]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,

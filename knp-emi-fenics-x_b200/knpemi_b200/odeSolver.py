@@ -457,8 +457,10 @@ class MembraneModel:
             self._inflight = (pend, bound)         # keep the arrays alive until the copies are done
             rc = self._lib.kem_step_io(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
                                        n_stim, cols, vals, len(pend), a_in, len(bound), a_out, None, None)
-            if rc != 0:
+            if rc != 0:                            # nothing was enqueued: the recorded writes stay recorded
                 self._prefetched = {}
+                pend.update(self._pending)
+                self._pending = pend
             check(rc, "kem_step_io")
         else:
             check(self._lib.kem_step(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
