@@ -93,7 +93,7 @@ kem_step_kernel(const __grid_constant__ KemArgs<M> a)
         const int n_tt = (2 * a.n_sub + 2) * NT;
         for (int k = threadIdx.x; k < n_tt; k += BLOCK) s_tt[k] = a.ttab[k];
     }
-    kem::load_tables();
+    kem::load_tables<M::USES_LOG>();
     __syncthreads();
 
     const long long i = (long long)blockIdx.x * BLOCK + threadIdx.x;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(BLOCK)
 kem_step_dp45_kernel(const __grid_constant__ KemArgs<M> a)
 {
     constexpr int NS = M::NS, NOUT = M::NOUT, NT = M::NT;
-    kem::load_tables();
+    kem::load_tables<true>();          // the step-size controller takes a logarithm
     __syncthreads();
     const long long tid = (long long)blockIdx.x * BLOCK + threadIdx.x;
     if (tid >= a.n) return;

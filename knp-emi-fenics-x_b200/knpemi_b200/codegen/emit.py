@@ -24,7 +24,7 @@ from dataclasses import dataclass
 from .ir import P, S, T, Dag, ModelSourceError
 from .parse import ParsedModel
 
-CODEGEN_VERSION = "12"
+CODEGEN_VERSION = "13"
 
 
 @dataclass
@@ -330,6 +330,7 @@ class _Emitter:
         w(f"    static constexpr int NS = {self.ns}, NP = {self.np}, NOUT = {len(self.out_cols)}, "
           f"NT = {len(time_front)};")
         w(f"    static constexpr int DEFAULT_BLOCK = {self.opts.default_block};")
+        w("    static constexpr bool USES_LOG = @@USES_LOG@@;   // load the log table into shared memory")
         n_loop_ops = sum(1 for nid in order_dy if self.klass(nid) == "dyn"
                          and dag.nodes[nid].op not in ("const", "iconst", "param", "state", "time"))
         w(f"    static constexpr int STAGE_UNROLL = {4 if n_loop_ops <= self.opts.unroll_below else 1};"
@@ -416,6 +417,7 @@ class _Emitter:
         else:
             table = ""
         body = "\n".join(L).replace("@@CONST_TABLE@@", table)
+        body = body.replace("@@USES_LOG@@", "true" if "kem::log(" in body else "false")
         # hash of the code proper: the leading "// ..." lines (generator version, options) are
         # left out so that a generator release that emits the same code keeps the same hash
         code = "\n".join(ln for ln in body.split("\n") if not ln.startswith("// GENERATED by"))

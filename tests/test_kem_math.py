@@ -74,10 +74,12 @@ def test_removable_singularity_form_stays_comparable(hostlib):
         assert abs(got - ref) / abs(ref) < 2.3e-16 / abs(x) * 2
 
 
-@pytest.mark.parametrize("which,name,bound", [(0, "log", 1.0), (1, "sqrt", 0.5 + 1e-9), (2, "pow15", 1.3)])
+@pytest.mark.parametrize("which,name,bound", [(0, "log", 1.7), (1, "sqrt", 0.5 + 1e-9), (2, "pow15", 1.3)])
 @pytest.mark.parametrize("emax", [1, 60, 600])
 def test_log_sqrt_pow15_accuracy(hostlib, which, name, bound, emax):
-    """log < 1 ulp; sqrt correctly rounded; x**1.5 = x*sqrt(x) <= 1.3 ulp (CUDA pow: 2 ulp)."""
+    """table-assisted log <= 1.6 ulp (one rounding each for the table entry, k ln2 + logc and the
+    final sum; also relative to itself as x -> 1); sqrt correctly rounded; x**1.5 = x*sqrt(x) <= 1.3 ulp
+    (CUDA pow: 2 ulp)."""
     assert hostlib.kem_check_unary(which, 300000, emax, 11) <= bound
 
 
