@@ -186,6 +186,15 @@ def test_page_locked_ranges_are_checked_end_to_end(built):
     check(lib.kem_host_register(C.c_void_p(big.ctypes.data), big.nbytes), "kem_host_register")
     check(lib.kem_host_unregister(C.c_void_p(big.ctypes.data)), "kem_host_unregister")
     assert host_is_pinned(big)
+    # a view INSIDE the registered range shares the owner's page-lock: registering it counts a
+    # reference on the owner, unregistering it gives that reference back
+    inner = big[16:400]
+    check(lib.kem_host_register(C.c_void_p(inner.ctypes.data), inner.nbytes), "kem_host_register")
+    check(lib.kem_host_unregister(C.c_void_p(big.ctypes.data)), "kem_host_unregister")
+    assert host_is_pinned(big)                                   # still held through the view
+    check(lib.kem_host_register(C.c_void_p(big.ctypes.data), big.nbytes), "kem_host_register")
+    check(lib.kem_host_unregister(C.c_void_p(inner.ctypes.data)), "kem_host_unregister")
+    assert host_is_pinned(big)
     # overlapping a registered range from another base is refused, not swallowed
     with pytest.raises(KemError, match="overlap"):
         check(lib.kem_host_register(C.c_void_p(big.ctypes.data + 8 * 50), big.nbytes), "kem_host_register")
