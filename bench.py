@@ -14,12 +14,18 @@ path).  Its working set (1.1 GB per GPU) is larger than the 126 MB L2, so no L2
 flush is needed between iterations.
 
 One JSON line on stdout (rank 0).  `value` is measured with inputs resident in
-HBM and CUDA events on the launching stream; `e2e` goes through the public
-MembraneModel API with pinned HOST buffers, host<->device copies inside the
-timed region; `roofline` states the FP64-pipe issue-slot utilisation of the
-fused kernel against a DFMA peak measured in the same run (MEASURED_PEAKS.json
-has no fp64 entry) plus the HBM view; `cpu_baseline` is the oracle port of the
-reference's stepping on the host cores (rank 0, N = 1 only).
+HBM and CUDA events on the launching stream (`sustained`: the same loop for at
+least a second); `e2e` goes through the public MembraneModel API
+(`step_exchange`) with pinned HOST buffers, host<->device copies inside the
+timed region -- `e2e.link` is the same copies with nothing else (the host-link
+floor, measured in the same run, all ranks at once) and `e2e.dropin` the
+reference's unmodified 7-setter + step + 4-getter call sequence; `roofline`
+states the FP64-pipe issue-slot utilisation of the fused kernel against a DFMA
+peak measured in the same run (MEASURED_PEAKS.json has no fp64 entry) plus the
+HBM view; `parity_sample` steps 10^5 random DOFs of the workload on the GPU
+and in the oracle; `cpu_baseline` is the oracle port of the reference's
+stepping on the host cores (rank 0, N = 1 only).  `--workload tissue_1e8` is
+BASELINE.json configs[4]: two membrane models, 10^8 DOFs, strong scaling.
 """
 from __future__ import annotations
 
