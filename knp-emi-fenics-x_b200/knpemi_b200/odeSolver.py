@@ -18,7 +18,13 @@ What differs, deliberately (SURVEY.md sections 0 and 8):
   O3 (Dormand-Prince 5(4) at the reference's LSODA tolerances) instead;
 * model defaults are read once instead of N times (odeSolver.py:41-42), locator
   masks are evaluated vectorised when that provably gives the per-row answer, and
-  cached per callable.
+  cached per callable for as long as the callable still answers the same on a
+  sample of rows (the reference re-evaluates it at every call, odeSolver.py:100);
+* caller arrays that come back every step (the getter targets of solve_odes) are
+  page-locked on their second sighting, columns the generated right-hand side never
+  reads follow the ``unread_inputs`` policy, output slots it assigns a literal are
+  filled on the host; ``exchange="deferred"`` is the opt-in that pipelines the
+  setter / getter copies with the kernel (see ``MembraneModel.__init__``).
 
 There is no CPU path: construction raises if libknpemi_b200.so or a CUDA device
 is missing.
