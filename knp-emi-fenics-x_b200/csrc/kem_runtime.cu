@@ -292,6 +292,11 @@ const int IO_TARGET_CHUNKS = [] {       // 16: measured best of 8/16/32/64 at 1e
     return e && atoi(e) > 0 ? atoi(e) : 16;
 }();
 constexpr int64_t IO_MIN_CHUNK = 1 << 16;   // smallest tail chunk of the pipeline (0.5 MB per column)
+// Columns below this size always go through the pinned staging buffer: one memcpy of a few KB
+// costs less than asking the driver (twice) whether the caller's memory is page-locked.  The
+// reference's real meshes have 124 - 2 952 membrane DOFs (1 - 24 KB per column), where the
+// per-call latency of the setters and getters is what a PDE step pays.
+constexpr size_t DIRECT_COPY_MIN_BYTES = 64 * 1024;
 
 struct Shard {
     int dev = 0;
@@ -319,6 +324,8 @@ struct Shard {
     // pinned staging for pageable host columns
     void *h_stage[N_STAGE] = {};
     cudaEvent_t stage_ev[N_STAGE] = {};
+    bool stage_busy[N_STAGE] = {};    // a host->device DMA out of this slot may still be in flight
+    int stage_next = 0;
     // per-chunk events of kem_step_io / a chunked kem_step
     std::vector<cudaEvent_t> io_in, io_k0, io_k1, io_out, io_in2;
     // DOF chunks of the last chunked step; `chunks_live` while nothing else has been enqueued
@@ -458,20 +465,22 @@ int copy_in(Shard &s, double *dst, const double *src, size_t bytes, cudaStream_t
     }
     int rc = ensure_stage(s);
     if (rc) return rc;
+    // The slots rotate across calls and a slot is waited for only when it comes round again:
+    // the source has been consumed once it is in the staging buffer, so a run of small setter
+    // calls (seven per PDE step, a few KB each on the reference's real meshes) never blocks on
+    // its own DMAs.
     size_t off = 0;
-    int k = 0;
     while (off < bytes) {
         const size_t len = std::min(STAGE_BYTES, bytes - off);
-        const int slot = k % N_STAGE;
-        if (k >= N_STAGE) CK(cudaEventSynchronize(s.stage_ev[slot]));
+        const int slot = s.stage_next;
+        s.stage_next = (slot + 1) % N_STAGE;
+        if (s.stage_busy[slot]) CK(cudaEventSynchronize(s.stage_ev[slot]));
         CopyPool::get().copy(s.h_stage[slot], (const char *)src + off, len);
         CK(cudaMemcpyAsync((char *)dst + off, s.h_stage[slot], len, cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(s.stage_ev[slot], st));
+        s.stage_busy[slot] = true;
         off += len;
-        ++k;
     }
-    // the staging slots may be reused by the next call: wait for the DMAs
-    for (int j = 0; j < std::min(k, N_STAGE); ++j) CK(cudaEventSynchronize(s.stage_ev[j]));
     return KEM_OK;
 }
 
@@ -486,6 +495,11 @@ int copy_out(Shard &s, double *dst, const double *src, size_t bytes, cudaStream_
     }
     int rc = ensure_stage(s);
     if (rc) return rc;
+    for (int j = 0; j < N_STAGE; ++j)          // uploads that still read from the staging slots
+        if (s.stage_busy[j]) {
+            CK(cudaEventSynchronize(s.stage_ev[j]));
+            s.stage_busy[j] = false;
+        }
     const size_t n_chunks = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
     for (size_t k = 0; k < n_chunks + N_STAGE; ++k) {
         const int slot = (int)(k % N_STAGE);
@@ -1247,7 +1261,8 @@ int kem_set_column(kem_handle h, int kind, int col, const double *src, int64_t n
     ARG(n == h->n, "length must equal the handle's n_dof");
     ARG(src || n == 0, "null source");
     if (n == 0) return KEM_OK;
-    const bool pinned = is_pinned(src, (size_t)n * sizeof(double));
+    const size_t col_bytes = (size_t)n * sizeof(double);
+    const bool pinned = col_bytes >= DIRECT_COPY_MIN_BYTES && is_pinned(src, col_bytes);
     touch_param(h, kind, col);
     if (kind == KEM_PARAM && h->p_dead[col]) {
         switch (unread_destination(h, false, pinned)) {
@@ -1379,7 +1394,8 @@ int kem_get_column(kem_handle h, int kind, int col, double *dst, int64_t n)
     if (kind == KEM_PARAM && h->p_discarded[col])
         return fail(KEM_E_ARG, "kem_get_column: parameter column " + std::to_string(col) +
                                    " was discarded (KEM_UNREAD_DISCARD); its value is not kept");
-    const bool pinned = is_pinned(dst, (size_t)n * sizeof(double));
+    const size_t col_bytes = (size_t)n * sizeof(double);
+    const bool pinned = col_bytes >= DIRECT_COPY_MIN_BYTES && is_pinned(dst, col_bytes);
     for (Shard &s : h->shards) {
         if (s.n == 0) continue;
         if (pinned && s.chunks_live) {
