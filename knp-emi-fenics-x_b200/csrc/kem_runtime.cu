@@ -363,12 +363,6 @@ struct kem_handle_s {
     bool shadow_pinned_io = true;     // KEM_UNREAD_AUTO: pinned inputs of kem_step_io to dead slots are shadowed
     std::vector<char> out_const_valid;   // per constant output slot: 1 = the column holds the literal
     int step_chunks = 1;              // kem_step: launch the range as this many chunks (getter overlap)
-    // Small membranes (a column below DIRECT_COPY_MIN_BYTES): the first getter after a change
-    // fetches every state and output column with ONE wait into this pinned host copy; the
-    // getters that follow (solve_odes asks for V and three currents, run_2D.py:105-109) are a
-    // memcpy.  Valid until anything writes to the tables.
-    double *small_cache = nullptr;    // [ns + n_out][n], pinned
-    bool small_cache_valid = false;
     int io_chunks = 0;                // kem_step_io: chunks per shard (0 = IO_TARGET_CHUNKS / KNPEMI_IO_CHUNKS)
     int io_h2d_streams = 0;           // kem_step_io: 1 or 2 host->device streams (0 = default / KNPEMI_IO_H2D_STREAMS)
     bool uni_dirty = true;
@@ -703,43 +697,6 @@ int ensure_chunk_events(Shard &s, size_t n_chunks)
 void drop_live_chunks(kem_handle h)
 {
     for (Shard &s : h->shards) s.chunks_live = false;
-    h->small_cache_valid = false;      // (every writer to the tables passes through here)
-}
-
-// slot of a column in the small-membrane getter cache, or -1 (uniform / host-side columns and
-// parameters that are not outputs are not cached)
-int small_cache_slot(kem_handle h, int kind, int col)
-{
-    if (kind == KEM_STATE) return col;
-    for (int k = 0; k < h->m->n_out; ++k)
-        if (h->m->out_cols[k] == col) return h->m->ns + k;
-    return -1;
-}
-
-int fill_small_cache(kem_handle h)
-{
-    const KemModelDesc *m = h->m;
-    const size_t n = (size_t)h->n;
-    if (!h->small_cache)
-        CK(cudaHostAlloc((void **)&h->small_cache, (size_t)(m->ns + std::max(m->n_out, 1)) * n * sizeof(double),
-                         cudaHostAllocPortable));
-    for (Shard &s : h->shards) {
-        if (s.n == 0) continue;
-        CK(cudaSetDevice(s.dev));
-        for (int c = 0; c < m->ns; ++c)
-            CK(cudaMemcpyAsync(h->small_cache + (size_t)c * n + s.begin, s.ycol[c], (size_t)s.n * sizeof(double),
-                               cudaMemcpyDeviceToHost, s.stream));
-        for (int k = 0; k < m->n_out; ++k)
-            CK(cudaMemcpyAsync(h->small_cache + (size_t)(m->ns + k) * n + s.begin, s.pcol[m->out_cols[k]],
-                               (size_t)s.n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-    }
-    for (Shard &s : h->shards) {
-        if (s.n == 0) continue;
-        CK(cudaSetDevice(s.dev));
-        CK(cudaStreamSynchronize(s.stream));
-    }
-    h->small_cache_valid = true;
-    return KEM_OK;
 }
 
 int const_out_index(kem_handle h, int kind, int col)
@@ -761,7 +718,6 @@ void touch_param(kem_handle h, int kind, int col)
 void mark_outputs_stored(kem_handle h)
 {
     std::fill(h->out_const_valid.begin(), h->out_const_valid.end(), 1);
-    h->small_cache_valid = false;
 }
 
 bool holds_literal(kem_handle h, int kind, int col, double *v)
@@ -1243,7 +1199,6 @@ int kem_destroy(kem_handle h)
         if (s.stream2) cudaStreamDestroy(s.stream2);
         if (s.s_out) cudaStreamDestroy(s.s_out);
     }
-    if (h->small_cache) cudaFreeHost(h->small_cache);
     cudaGetLastError();
     delete h;
     return KEM_OK;
@@ -1440,17 +1395,6 @@ int kem_get_column(kem_handle h, int kind, int col, double *dst, int64_t n)
         return fail(KEM_E_ARG, "kem_get_column: parameter column " + std::to_string(col) +
                                    " was discarded (KEM_UNREAD_DISCARD); its value is not kept");
     const size_t col_bytes = (size_t)n * sizeof(double);
-    if (col_bytes < DIRECT_COPY_MIN_BYTES) {
-        const int slot = small_cache_slot(h, kind, col);
-        if (slot >= 0) {
-            if (!h->small_cache_valid) {
-                rc = fill_small_cache(h);
-                if (rc) return rc;
-            }
-            memcpy(dst, h->small_cache + (size_t)slot * (size_t)n, col_bytes);
-            return KEM_OK;
-        }
-    }
     const bool pinned = col_bytes >= DIRECT_COPY_MIN_BYTES && is_pinned(dst, col_bytes);
     for (Shard &s : h->shards) {
         if (s.n == 0) continue;
