@@ -209,3 +209,27 @@ def test_host_array_cache_registers_on_the_second_sighting_of_a_living_owner(mon
     assert len(fake.log) == n_calls
     cache.release_all()
     assert not fake.registered and not cache.pinned
+
+
+def test_eliminated_ion_terms_follow_the_reference_expression():
+    """update_pde_variables (utils.py:249-258): c_elim_sum = -(1/z_e) rho_z rho_tag, then
+    += -(1/z_e) z_k c_k per solved ion.  The device kernels take the constant and the coefficients
+    formed exactly like that."""
+    from knpemi_b200.device_updates import eliminated_ion_terms
+    ion_list = [{"name": "K", "z": 1.0}, {"name": "Cl", "z": -1.0}, {"name": "Na", "z": 1.0}]   # run_2D.py:252
+    rho_z, rho_tag = -1.0, 41.3
+    a0, coefs = eliminated_ion_terms(ion_list, rho_z, rho_tag)
+    z_e = ion_list[-1]["z"]
+    assert a0 == -(1.0 / z_e) * rho_z * rho_tag
+    assert coefs == [-(1.0 / z_e) * 1.0, -(1.0 / z_e) * -1.0]
+    rng = np.random.default_rng(0)
+    c_K, c_Cl = rng.uniform(1, 150, 50), rng.uniform(1, 150, 50)
+    want = a0
+    for ion, c in zip(ion_list[:-1], (c_K, c_Cl)):            # the reference's loop, term by term
+        want = want + -(1.0 / z_e) * ion["z"] * c
+    assert np.array_equal(a0 + coefs[0] * c_K + coefs[1] * c_Cl, want)
+    # electroneutrality: z_e c_elim + sum z_k c_k + rho_z rho_tag = 0
+    assert np.allclose(z_e * want + c_K - c_Cl + rho_z * rho_tag, 0.0, atol=1e-12)
+    with pytest.raises(Exception):
+        from knpemi_b200.device_updates import _pack
+        _pack([(1.0, 8)] * 9)
