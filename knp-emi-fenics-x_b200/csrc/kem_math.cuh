@@ -277,7 +277,8 @@ KEM_HD double sqrt(double x)
     h = fma(h, r, h);
     const double d = fma(-g, g, x);
     const double res = fma(d, h, g);
-    return ((double_to_bits(x) << 1) == 0) ? x : res;
+    const uint64_t bx = double_to_bits(x);
+    return ((((uint32_t)(bx >> 32) & 0x7fffffffu) | (uint32_t)bx) == 0u) ? x : res;
 }
 
 // x^1.5 = x sqrt(x): two roundings, <= 1 ulp (CUDA's pow is specified to 2 ulp).
@@ -285,9 +286,12 @@ KEM_HD double pow15(double x) { return x * kem::sqrt(x); }
 
 // ---- log -------------------------------------------------------------------------------
 // Table-assisted (round 2): x = 2^k m with m in [0.70703125, 1.4140625) -- the halving threshold
-// sits on a table boundary (mantissa 0x6a000) instead of exactly sqrt 2 --, j = top 8 mantissa
-// bits of x selects (invc_j, logc_j) from a 4 KB table in shared memory: invc_j ~ 1 / centre of
-// the interval, logc_j = -log(invc_j) of the ROUNDED invc_j, so that
+// sits on a table boundary (mantissa 0x6a000) instead of exactly sqrt 2.  With
+// t = (high word of x) - 0x3fe6a000 the exponent is k = t >> 20, the table index
+// j = (t >> 12) & 255 (entries ordered by m) and m's high word is that of x minus t's exponent
+// bits: five integer instructions.  Entry j of a 4 KB table in shared memory holds
+// (invc_j, logc_j): invc_j ~ 1 / centre of the interval, logc_j = -log(invc_j) of the ROUNDED
+// invc_j, so that
 //     log(x) = k ln2 + logc_j + log1p(r),   r = m invc_j - 1   (one FMA, |r| <= 2^-8)
 // holds exactly; the two intervals next to 1 use invc = 1, logc = 0, i.e. r = m - 1, which keeps
 // the result accurate relative to itself as x -> 1.  log1p(r) = r - r^2/2 + r^3 q(r), q of degree
@@ -299,59 +303,6 @@ KEM_HD double pow15(double x) { return x * kem::sqrt(x); }
 // log(+inf) = +inf, log(x < 0) = log(NaN) = NaN, for one 32-bit select on the normal path.
 #define KEM_LOG_TABLE_SIZE 256
 #define KEM_LOG_TABLE_VALUES \
-    {0x1.0000000000000p+0, 0x0.0p+0}, {0x1.fd04794a10e6ap-1, 0x1.7ee11ebd82ec4p-8},         \
-    {0x1.fb0c610d5e939p-1, 0x1.3e7295d25a7d5p-7}, {0x1.f9182b6813bafp-1, 0x1.bcf712c743853p-7}, \
-    {0x1.f727cce5f530ap-1, 0x1.1d7f7eb9eebf1p-6}, {0x1.f53b3a3fa204ep-1, 0x1.5c45a51b8d393p-6}, \
-    {0x1.f3526859b8cecp-1, 0x1.9ace7551cc515p-6}, {0x1.f16d4c4401f17p-1, 0x1.d91a66c543cbep-6}, \
-    {0x1.ef8bdb389ebadp-1, 0x1.0b94f7c196173p-5}, {0x1.edae0a9b3d3a5p-1, 0x1.2a7ec2214e879p-5}, \
-    {0x1.ebd3cff850b0cp-1, 0x1.494acc34d911dp-5}, {0x1.e9fd21044e799p-1, 0x1.67f94f094bd92p-5}, \
-    {0x1.e829f39aef509p-1, 0x1.868a83083f6d0p-5}, {0x1.e65a3dbe74d6bp-1, 0x1.a4fe9ffa3d233p-5}, \
-    {0x1.e48df596f3394p-1, 0x1.c355dd0921f2fp-5}, {0x1.e2c511719ee16p-1, 0x1.e19070c276010p-5}, \
-    {0x1.e0ff87c01e100p-1, 0x1.ffae9119b92fbp-5}, {0x1.df3d4f17de4dbp-1, 0x1.0ed839b5526fep-4}, \
-    {0x1.dd7e5e316d94cp-1, 0x1.1dcb263db1944p-4}, {0x1.dbc2abe7d71d4p-1, 0x1.2cb0283f5de22p-4}, \
-    {0x1.da0a2f3803b41p-1, 0x1.3b87598b1b6f0p-4}, {0x1.d854df401d855p-1, 0x1.4a50d3aa1b03fp-4}, \
-    {0x1.d6a2b33ef7448p-1, 0x1.590cafdf01c26p-4}, {0x1.d4f3a293769cap-1, 0x1.67bb0726ec0fbp-4}, \
-    {0x1.d347a4bc01d34p-1, 0x1.765bf23a6be17p-4}, {0x1.d19eb155f08a4p-1, 0x1.84ef898e82828p-4}, \
-    {0x1.cff8c01cff8c0p-1, 0x1.9375e55595edfp-4}, {0x1.ce55c8eac7900p-1, 0x1.a1ef1d8061cd8p-4}, \
-    {0x1.ccb5c3b636e3ap-1, 0x1.b05b49bee4403p-4}, {0x1.cb18a8930de60p-1, 0x1.beba818146764p-4}, \
-    {0x1.c97e6fb15e44dp-1, 0x1.cd0cdbf8c13e0p-4}, {0x1.c7e7115d0ce95p-1, 0x1.db5270187d925p-4}, \
-    {0x1.c65285fd56843p-1, 0x1.e98b54967146bp-4}, {0x1.c4c0c61456a8ep-1, 0x1.f7b79fec37de2p-4}, \
-    {0x1.c331ca3e91679p-1, 0x1.02ebb42bf3d4ap-3}, {0x1.c1a58b327f576p-1, 0x1.09f561ee719c4p-3}, \
-    {0x1.c01c01c01c01cp-1, 0x1.10f8e422539b1p-3}, {0x1.be9526d0769fap-1, 0x1.17f6458fca611p-3}, \
-    {0x1.bd10f365451b6p-1, 0x1.1eed90e2dc2c3p-3}, {0x1.bb8f609879493p-1, 0x1.25ded0abc6ad3p-3}, \
-    {0x1.ba10679bd8488p-1, 0x1.2cca0f5f5f252p-3}, {0x1.b89401b89401cp-1, 0x1.33af575770e4dp-3}, \
-    {0x1.b71a284ee6b34p-1, 0x1.3a8eb2d31a375p-3}, {0x1.b5a2d4d5b081fp-1, 0x1.41682bf727bbfp-3}, \
-    {0x1.b42e00da17007p-1, 0x1.483bccce6e3dcp-3}, {0x1.b2bba5ff26a23p-1, 0x1.4f099f4a230b1p-3}, \
-    {0x1.b14bbdfd760e6p-1, 0x1.55d1ad4232d70p-3}, {0x1.afde42a2cb482p-1, 0x1.5c940075972b9p-3}, \
-    {0x1.ae732dd1c2a09p-1, 0x1.6350a28aaa759p-3}, {0x1.ad0a798177693p-1, 0x1.6a079d0f7aad0p-3}, \
-    {0x1.aba41fbd2e5b1p-1, 0x1.70b8f97a1aa74p-3}, {0x1.aa401aa401aa4p-1, 0x1.7764c128f2127p-3}, \
-    {0x1.a8de64688ebabp-1, 0x1.7e0afd630c276p-3}, {0x1.a77ef750a56dap-1, 0x1.84abb75865137p-3}, \
-    {0x1.a621cdb4f8fdfp-1, 0x1.8b46f8223625bp-3}, {0x1.a4c6e200d2637p-1, 0x1.91dcc8c340bdfp-3}, \
-    {0x1.a36e2eb1c432dp-1, 0x1.986d3228180c8p-3}, {0x1.a217ae575ff2fp-1, 0x1.9ef83d2769a34p-3}, \
-    {0x1.a0c35b92ecdf1p-1, 0x1.a57df28244dcbp-3}, {0x1.9f713117200d0p-1, 0x1.abfe5ae46124ap-3}, \
-    {0x1.9e2129a7d5f0ap-1, 0x1.b2797ee46320cp-3}, {0x1.9cd34019cd340p-1, 0x1.b8ef670420c3bp-3}, \
-    {0x1.9b876f5262dd1p-1, 0x1.bf601bb0e44e0p-3}, {0x1.9a3db2474fb98p-1, 0x1.c5cba543ae424p-3}, \
-    {0x1.98f603fe670a0p-1, 0x1.cc320c0176501p-3}, {0x1.97b05f8d56652p-1, 0x1.d293581b6b3e7p-3}, \
-    {0x1.966cc01966cc0p-1, 0x1.d8ef91af31d5ep-3}, {0x1.952b20d73ee97p-1, 0x1.df46c0c722d30p-3}, \
-    {0x1.93eb7d0aa6759p-1, 0x1.e598ed5a87e2ep-3}, {0x1.92add0064ab74p-1, 0x1.ebe61f4dd7b0bp-3}, \
-    {0x1.9172152b841ddp-1, 0x1.f22e5e72f105cp-3}, {0x1.903847ea1cec1p-1, 0x1.f871b28955045p-3}, \
-    {0x1.8f0063c018f00p-1, 0x1.feb0233e607cep-3}, {0x1.8dca64397e408p-1, 0x1.0274dc16c232fp-2}, \
-    {0x1.8c9644f01efbcp-1, 0x1.058f3c703ebc5p-2}, {0x1.8b64018b64019p-1, 0x1.08a73667c57aep-2}, \
-    {0x1.8a3395c018a34p-1, 0x1.0bbccdb0d24bcp-2}, {0x1.8904fd503744bp-1, 0x1.0ed005f657da5p-2}, \
-    {0x1.87d8340ab6e97p-1, 0x1.11e0e2dad9cb6p-2}, {0x1.86ad35cb59a84p-1, 0x1.14ef67f88685ap-2}, \
-    {0x1.8583fe7a7c018p-1, 0x1.17fb98e15095ep-2}, {0x1.845c8a0ce5129p-1, 0x1.1b05791f07b4ap-2}, \
-    {0x1.8336d48397a24p-1, 0x1.1e0d0c33716bdp-2}, {0x1.8212d9eba4018p-1, 0x1.211255986160cp-2}, \
-    {0x1.80f0965dfabcbp-1, 0x1.241558bfd1405p-2}, {0x1.7fd005ff40180p-1, 0x1.27161913f853dp-2}, \
-    {0x1.7eb124ffa053bp-1, 0x1.2a1499f762bcap-2}, {0x1.7d93ef9aa4b46p-1, 0x1.2d10dec508582p-2}, \
-    {0x1.7c7862170949fp-1, 0x1.300aead06350cp-2}, {0x1.7b5e78c693733p-1, 0x1.3302c1658658ap-2}, \
-    {0x1.7a463005e918cp-1, 0x1.35f865c93293ep-2}, {0x1.792f843c689c3p-1, 0x1.38ebdb38ed320p-2}, \
-    {0x1.781a71dc01782p-1, 0x1.3bdd24eb14b69p-2}, {0x1.7706f5610d8d0p-1, 0x1.3ecc460ef5f50p-2}, \
-    {0x1.75f50b522b17cp-1, 0x1.41b941cce0beep-2}, {0x1.74e4b040174e5p-1, 0x1.44a41b463c47bp-2}, \
-    {0x1.73d5e0c5899f7p-1, 0x1.478cd5959b3d8p-2}, {0x1.72c899870f91fp-1, 0x1.4a7373cecf997p-2}, \
-    {0x1.71bcd732e940ap-1, 0x1.4d57f8fefe27fp-2}, {0x1.70b29680e66fap-1, 0x1.503a682cb1cb3p-2}, \
-    {0x1.6fa9d43244380p-1, 0x1.531ac457ee77fp-2}, {0x1.6ea28d118b474p-1, 0x1.55f9107a43ee2p-2}, \
-    {0x1.6d9cbdf26eaefp-1, 0x1.58d54f86e02f3p-2}, {0x1.6c9863b1ab429p-1, 0x1.5baf846aa1b1ap-2}, \
-    {0x1.6b957b34e7803p-1, 0x1.5e87b20c2954ap-2}, {0x1.6a94016a94017p-1, 0x1.615ddb4bec13cp-2}, \
     {0x1.6993f349cc726p+0, -0x1.61965cdb02c1ep-2}, {0x1.68954dd2390bap+0, -0x1.5ec433d5c35aep-2}, \
     {0x1.67980e0bf08c7p+0, -0x1.5bf406b543db1p-2}, {0x1.669c31075ab40p+0, -0x1.5925d2b112a59p-2}, \
     {0x1.65a1b3dd13357p+0, -0x1.565995069514cp-2}, {0x1.64a893adcd25fp+0, -0x1.538f4af8f72fcp-2}, \
@@ -426,7 +377,60 @@ KEM_HD double pow15(double x) { return x * kem::sqrt(x); }
     {0x1.03ce4584b19a0p+0, -0x1.e38ce30333100p-7}, {0x1.034ab2c50040dp+0, -0x1.a2a9c6c17044dp-7}, \
     {0x1.02c7a505cffbfp+0, -0x1.61e77e8b53f9fp-7}, {0x1.02451b7ddb2d2p+0, -0x1.2145e939ef1bcp-7}, \
     {0x1.01c315657186bp+0, -0x1.c189cbb0e283fp-8}, {0x1.014191f674111p+0, -0x1.40c8a7478788dp-8}, \
-    {0x1.00c0906c513cfp+0, -0x1.809048289860ap-9}, {0x1.0000000000000p+0, 0x0.0p+0}
+    {0x1.00c0906c513cfp+0, -0x1.809048289860ap-9}, {0x1.0000000000000p+0, 0x0.0p+0},        \
+    {0x1.0000000000000p+0, 0x0.0p+0}, {0x1.fd04794a10e6ap-1, 0x1.7ee11ebd82ec4p-8},         \
+    {0x1.fb0c610d5e939p-1, 0x1.3e7295d25a7d5p-7}, {0x1.f9182b6813bafp-1, 0x1.bcf712c743853p-7}, \
+    {0x1.f727cce5f530ap-1, 0x1.1d7f7eb9eebf1p-6}, {0x1.f53b3a3fa204ep-1, 0x1.5c45a51b8d393p-6}, \
+    {0x1.f3526859b8cecp-1, 0x1.9ace7551cc515p-6}, {0x1.f16d4c4401f17p-1, 0x1.d91a66c543cbep-6}, \
+    {0x1.ef8bdb389ebadp-1, 0x1.0b94f7c196173p-5}, {0x1.edae0a9b3d3a5p-1, 0x1.2a7ec2214e879p-5}, \
+    {0x1.ebd3cff850b0cp-1, 0x1.494acc34d911dp-5}, {0x1.e9fd21044e799p-1, 0x1.67f94f094bd92p-5}, \
+    {0x1.e829f39aef509p-1, 0x1.868a83083f6d0p-5}, {0x1.e65a3dbe74d6bp-1, 0x1.a4fe9ffa3d233p-5}, \
+    {0x1.e48df596f3394p-1, 0x1.c355dd0921f2fp-5}, {0x1.e2c511719ee16p-1, 0x1.e19070c276010p-5}, \
+    {0x1.e0ff87c01e100p-1, 0x1.ffae9119b92fbp-5}, {0x1.df3d4f17de4dbp-1, 0x1.0ed839b5526fep-4}, \
+    {0x1.dd7e5e316d94cp-1, 0x1.1dcb263db1944p-4}, {0x1.dbc2abe7d71d4p-1, 0x1.2cb0283f5de22p-4}, \
+    {0x1.da0a2f3803b41p-1, 0x1.3b87598b1b6f0p-4}, {0x1.d854df401d855p-1, 0x1.4a50d3aa1b03fp-4}, \
+    {0x1.d6a2b33ef7448p-1, 0x1.590cafdf01c26p-4}, {0x1.d4f3a293769cap-1, 0x1.67bb0726ec0fbp-4}, \
+    {0x1.d347a4bc01d34p-1, 0x1.765bf23a6be17p-4}, {0x1.d19eb155f08a4p-1, 0x1.84ef898e82828p-4}, \
+    {0x1.cff8c01cff8c0p-1, 0x1.9375e55595edfp-4}, {0x1.ce55c8eac7900p-1, 0x1.a1ef1d8061cd8p-4}, \
+    {0x1.ccb5c3b636e3ap-1, 0x1.b05b49bee4403p-4}, {0x1.cb18a8930de60p-1, 0x1.beba818146764p-4}, \
+    {0x1.c97e6fb15e44dp-1, 0x1.cd0cdbf8c13e0p-4}, {0x1.c7e7115d0ce95p-1, 0x1.db5270187d925p-4}, \
+    {0x1.c65285fd56843p-1, 0x1.e98b54967146bp-4}, {0x1.c4c0c61456a8ep-1, 0x1.f7b79fec37de2p-4}, \
+    {0x1.c331ca3e91679p-1, 0x1.02ebb42bf3d4ap-3}, {0x1.c1a58b327f576p-1, 0x1.09f561ee719c4p-3}, \
+    {0x1.c01c01c01c01cp-1, 0x1.10f8e422539b1p-3}, {0x1.be9526d0769fap-1, 0x1.17f6458fca611p-3}, \
+    {0x1.bd10f365451b6p-1, 0x1.1eed90e2dc2c3p-3}, {0x1.bb8f609879493p-1, 0x1.25ded0abc6ad3p-3}, \
+    {0x1.ba10679bd8488p-1, 0x1.2cca0f5f5f252p-3}, {0x1.b89401b89401cp-1, 0x1.33af575770e4dp-3}, \
+    {0x1.b71a284ee6b34p-1, 0x1.3a8eb2d31a375p-3}, {0x1.b5a2d4d5b081fp-1, 0x1.41682bf727bbfp-3}, \
+    {0x1.b42e00da17007p-1, 0x1.483bccce6e3dcp-3}, {0x1.b2bba5ff26a23p-1, 0x1.4f099f4a230b1p-3}, \
+    {0x1.b14bbdfd760e6p-1, 0x1.55d1ad4232d70p-3}, {0x1.afde42a2cb482p-1, 0x1.5c940075972b9p-3}, \
+    {0x1.ae732dd1c2a09p-1, 0x1.6350a28aaa759p-3}, {0x1.ad0a798177693p-1, 0x1.6a079d0f7aad0p-3}, \
+    {0x1.aba41fbd2e5b1p-1, 0x1.70b8f97a1aa74p-3}, {0x1.aa401aa401aa4p-1, 0x1.7764c128f2127p-3}, \
+    {0x1.a8de64688ebabp-1, 0x1.7e0afd630c276p-3}, {0x1.a77ef750a56dap-1, 0x1.84abb75865137p-3}, \
+    {0x1.a621cdb4f8fdfp-1, 0x1.8b46f8223625bp-3}, {0x1.a4c6e200d2637p-1, 0x1.91dcc8c340bdfp-3}, \
+    {0x1.a36e2eb1c432dp-1, 0x1.986d3228180c8p-3}, {0x1.a217ae575ff2fp-1, 0x1.9ef83d2769a34p-3}, \
+    {0x1.a0c35b92ecdf1p-1, 0x1.a57df28244dcbp-3}, {0x1.9f713117200d0p-1, 0x1.abfe5ae46124ap-3}, \
+    {0x1.9e2129a7d5f0ap-1, 0x1.b2797ee46320cp-3}, {0x1.9cd34019cd340p-1, 0x1.b8ef670420c3bp-3}, \
+    {0x1.9b876f5262dd1p-1, 0x1.bf601bb0e44e0p-3}, {0x1.9a3db2474fb98p-1, 0x1.c5cba543ae424p-3}, \
+    {0x1.98f603fe670a0p-1, 0x1.cc320c0176501p-3}, {0x1.97b05f8d56652p-1, 0x1.d293581b6b3e7p-3}, \
+    {0x1.966cc01966cc0p-1, 0x1.d8ef91af31d5ep-3}, {0x1.952b20d73ee97p-1, 0x1.df46c0c722d30p-3}, \
+    {0x1.93eb7d0aa6759p-1, 0x1.e598ed5a87e2ep-3}, {0x1.92add0064ab74p-1, 0x1.ebe61f4dd7b0bp-3}, \
+    {0x1.9172152b841ddp-1, 0x1.f22e5e72f105cp-3}, {0x1.903847ea1cec1p-1, 0x1.f871b28955045p-3}, \
+    {0x1.8f0063c018f00p-1, 0x1.feb0233e607cep-3}, {0x1.8dca64397e408p-1, 0x1.0274dc16c232fp-2}, \
+    {0x1.8c9644f01efbcp-1, 0x1.058f3c703ebc5p-2}, {0x1.8b64018b64019p-1, 0x1.08a73667c57aep-2}, \
+    {0x1.8a3395c018a34p-1, 0x1.0bbccdb0d24bcp-2}, {0x1.8904fd503744bp-1, 0x1.0ed005f657da5p-2}, \
+    {0x1.87d8340ab6e97p-1, 0x1.11e0e2dad9cb6p-2}, {0x1.86ad35cb59a84p-1, 0x1.14ef67f88685ap-2}, \
+    {0x1.8583fe7a7c018p-1, 0x1.17fb98e15095ep-2}, {0x1.845c8a0ce5129p-1, 0x1.1b05791f07b4ap-2}, \
+    {0x1.8336d48397a24p-1, 0x1.1e0d0c33716bdp-2}, {0x1.8212d9eba4018p-1, 0x1.211255986160cp-2}, \
+    {0x1.80f0965dfabcbp-1, 0x1.241558bfd1405p-2}, {0x1.7fd005ff40180p-1, 0x1.27161913f853dp-2}, \
+    {0x1.7eb124ffa053bp-1, 0x1.2a1499f762bcap-2}, {0x1.7d93ef9aa4b46p-1, 0x1.2d10dec508582p-2}, \
+    {0x1.7c7862170949fp-1, 0x1.300aead06350cp-2}, {0x1.7b5e78c693733p-1, 0x1.3302c1658658ap-2}, \
+    {0x1.7a463005e918cp-1, 0x1.35f865c93293ep-2}, {0x1.792f843c689c3p-1, 0x1.38ebdb38ed320p-2}, \
+    {0x1.781a71dc01782p-1, 0x1.3bdd24eb14b69p-2}, {0x1.7706f5610d8d0p-1, 0x1.3ecc460ef5f50p-2}, \
+    {0x1.75f50b522b17cp-1, 0x1.41b941cce0beep-2}, {0x1.74e4b040174e5p-1, 0x1.44a41b463c47bp-2}, \
+    {0x1.73d5e0c5899f7p-1, 0x1.478cd5959b3d8p-2}, {0x1.72c899870f91fp-1, 0x1.4a7373cecf997p-2}, \
+    {0x1.71bcd732e940ap-1, 0x1.4d57f8fefe27fp-2}, {0x1.70b29680e66fap-1, 0x1.503a682cb1cb3p-2}, \
+    {0x1.6fa9d43244380p-1, 0x1.531ac457ee77fp-2}, {0x1.6ea28d118b474p-1, 0x1.55f9107a43ee2p-2}, \
+    {0x1.6d9cbdf26eaefp-1, 0x1.58d54f86e02f3p-2}, {0x1.6c9863b1ab429p-1, 0x1.5baf846aa1b1ap-2}, \
+    {0x1.6b957b34e7803p-1, 0x1.5e87b20c2954ap-2}, {0x1.6a94016a94017p-1, 0x1.615ddb4bec13cp-2}
 
 #define KEM_LOG_CONSTS                                                                   \
     {0x1.62e42fee00000p-1,  /* [0] ln2 high: low 21 mantissa bits zero, k*ln2_hi exact */ \
@@ -473,13 +477,11 @@ KEM_HD double log(double x)
 {
     const uint64_t bx = double_to_bits(x);
     const int hx0 = (int)(uint32_t)(bx >> 32);
-    const int hx = hx0 & 0x000fffff;
-    int k = (hx0 >> 20) - 1023;
-    const int i = (hx + 0x96000) & 0x100000;          // mantissa >= 0x6a000 (1.4140625): halve it
-    k += i >> 20;
-    const uint64_t bm = ((uint64_t)(uint32_t)(hx | (i ^ 0x3ff00000)) << 32) | (bx & 0xFFFFFFFFull);
-    const double m = bits_to_double(bm);
-    const LogEntry T = KEM_LOG_T[hx >> 12];
+    const uint32_t t = (uint32_t)hx0 - 0x3fe6a000u;
+    const int k = (int)t >> 20;
+    const LogEntry T = KEM_LOG_T[(t >> 12) & (KEM_LOG_TABLE_SIZE - 1)];
+    const uint32_t mh = (uint32_t)hx0 - (t & 0xfff00000u);
+    const double m = bits_to_double(((uint64_t)mh << 32) | (bx & 0xFFFFFFFFull));
     const uint32_t dk_hi = (uint32_t)(double_to_bits((double)k) >> 32);        // ((double)k has a zero low word)
     const bool ordinary = (uint32_t)(hx0 - 0x00100000) < 0x7fe00000u;           // positive, normal, finite
     // (a NaN whose payload sits in the low word only is reported as +inf: still not finite)

@@ -1,10 +1,11 @@
 """Table and polynomial of the table-assisted log in csrc/kem_math.cuh.
 
 x = 2^k m with m in [0.70703125, 1.4140625) (the halving threshold sits on a table boundary,
-mantissa 0x6a000, instead of exactly sqrt 2); j = top 8 mantissa bits of x selects
-(invc_j, logc_j): invc_j ~ 1/centre of the interval, logc_j = -log(invc_j) of the ROUNDED invc_j,
+mantissa 0x6a000, instead of exactly sqrt 2).  With t = (high word of x) - 0x3fe6a000 the
+exponent is k = t >> 20 and the table index j = (t >> 12) & 255, i.e. the entries are ordered by
+m, from 0.70703125 (j = 0) through 1 (j = 150) to 1.4140625; entry j holds (invc_j, logc_j): invc_j ~ 1/centre of the interval, logc_j = -log(invc_j) of the ROUNDED invc_j,
 so that log(m) = logc_j + log1p(r) holds exactly for r = m invc_j - 1 (one FMA, exact up to its
-own rounding).  The two intervals next to 1 (j = 0 and j = 255) use invc = 1, logc = 0: r = m - 1,
+own rounding).  The two intervals next to 1 (j = 149 and j = 150) use invc = 1, logc = 0: r = m - 1,
 which keeps the result accurate relative to itself as x -> 1.  |r| <= 2^-8.
 log1p(r) = r - r^2/2 + r^3 q(r), q of degree 4 fitted at Chebyshev nodes in 60-digit arithmetic.
 Prints the C initialisers and the worst error of the polynomial relative to log1p(r).
@@ -12,7 +13,7 @@ Prints the C initialisers and the worst error of the polynomial relative to log1
 import mpmath as mp
 
 mp.mp.dps = 60
-N, HALVE = 256, 0x6a
+N, FIRST = 256, 0x6a          # entry j covers the mantissa bits (j + FIRST) mod 256; j < N - FIRST: halved
 a = mp.mpf(2) ** -8 * mp.mpf("1.002")
 n = 5
 nodes = [a * mp.cos(mp.pi * (2 * k + 1) / (2 * n)) for k in range(n)]
@@ -39,10 +40,11 @@ for k in range(-3000, 3001):
     worst = max(worst, abs(p - mp.log1p(r)) / abs(mp.log1p(r)))
 rows = []
 for j in range(N):
-    lo, hi = 1 + mp.mpf(j) / N, 1 + mp.mpf(j + 1) / N
-    if j >= HALVE:
+    b = (j + FIRST) % N
+    lo, hi = 1 + mp.mpf(b) / N, 1 + mp.mpf(b + 1) / N
+    if j < N - FIRST:
         lo, hi = lo / 2, hi / 2
-    if j in (0, N - 1):
+    if b in (0, N - 1):
         invc, logc = 1.0, 0.0
     else:
         invc = float(1 / ((lo + hi) / 2))
