@@ -157,6 +157,19 @@ def check(rc: int, what: str = "") -> int:
     raise KemError(f"{what or 'libknpemi_b200'} failed (code {rc}): {msg}")
 
 
+_from_buffer, _addressof = C.c_char.from_buffer, C.addressof
+
+
+def address(a: np.ndarray) -> int:
+    """Data pointer of a NumPy array, three times faster than ``a.ctypes.data`` (0.6 instead of
+    1.9 us: on a membrane of a few hundred DOFs the eleven setter / getter calls of a PDE step
+    are mostly interpreter time)."""
+    try:
+        return _addressof(_from_buffer(a))
+    except (TypeError, ValueError, BufferError):          # read-only, empty or strided array
+        return a.ctypes.data
+
+
 def device_count() -> int:
     n = C.c_int(0)
     rc = lib().kem_device_count(C.byref(n))

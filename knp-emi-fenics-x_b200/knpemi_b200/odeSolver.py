@@ -339,6 +339,8 @@ class MembraneModel:
         self.prefix = ode.__name__
         self.time = 0
 
+        self._col_cache = {}           # (what, name) -> (kind, column)
+        self._stim_cache = None        # (stimulus items, ctypes columns, ctypes values)
         self._mask_cache = {}          # id(locator) -> (locator, mask)
         self._registered = []          # host arrays page-locked by register_host_array
         self._pending = OrderedDict()  # exchange="deferred": (kind, col) -> (array, owner) not yet copied
@@ -455,11 +457,11 @@ class MembraneModel:
         if pend or bound:
             a_in = (kem_io_column * max(len(pend), 1))()
             for k, ((kind, col), (a, _owner)) in enumerate(pend.items()):
-                a_in[k].kind, a_in[k].col, a_in[k].host = kind, col, a.ctypes.data
+                a_in[k].kind, a_in[k].col, a_in[k].host = kind, col, _cabi.address(a)
             a_out = (kem_io_column * max(len(bound), 1))()
             for k, ((kind, col), (a, _owner)) in enumerate(bound.items()):
-                a_out[k].kind, a_out[k].col, a_out[k].host = kind, col, a.ctypes.data
-                self._prefetched[(kind, col)] = (a.ctypes.data, a.nbytes)
+                a_out[k].kind, a_out[k].col, a_out[k].host = kind, col, _cabi.address(a)
+                self._prefetched[(kind, col)] = (a_out[k].host, a.nbytes)
             self._inflight = (pend, bound)         # keep the arrays alive until the copies are done
             rc = self._lib.kem_step_io(self._h, float(self.time), float(dt), n_sub, self._scheme_id,
                                        n_stim, cols, vals, len(pend), a_in, len(bound), a_out, None, None)
@@ -534,7 +536,7 @@ class MembraneModel:
                 if self.auto_register:
                     _HOST_CACHE.sight(u, a)
                 keep.append(a)
-                arr[k].kind, arr[k].col, arr[k].host = kind, col, a.ctypes.data
+                arr[k].kind, arr[k].col, arr[k].host = kind, col, _cabi.address(a)
             return arr
 
         a_in, a_out = pack(inputs, False), pack(outputs, True)
@@ -697,11 +699,23 @@ class MembraneModel:
         return {"registers_per_thread": regs.value, "blocks_per_sm": nb.value}
 
     def _kind_col(self, what, which):
+        # (the per-call cost of the setters and getters is what a PDE step pays on the reference's
+        # real meshes of a few hundred DOFs: names are resolved once)
+        try:
+            return self._col_cache[(what, which)]
+        except (KeyError, TypeError, AttributeError):
+            pass
         if what == 'state':
-            return KEM_STATE, self.ode.state_indices(which)
-        if what == 'parameter':
-            return KEM_PARAM, self.ode.parameter_indices(which)
-        raise KeyError(what)
+            hit = (KEM_STATE, self.ode.state_indices(which))
+        elif what == 'parameter':
+            hit = (KEM_PARAM, self.ode.parameter_indices(which))
+        else:
+            raise KeyError(what)
+        try:
+            self._col_cache[(what, which)] = hit
+        except (TypeError, AttributeError):       # unhashable `which`, or a bare test object
+            pass
+        return hit
 
     def _host_array(self, u, writable):
         a = u.x.array if hasattr(u, "x") else u
@@ -729,11 +743,20 @@ class MembraneModel:
             self._stim_mask_key = key
             self._stim_mask_ref = mask
         n = len(stimulus)
+        try:
+            items = tuple(stimulus.items())
+            hit = getattr(self, "_stim_cache", None)
+            if hit is not None and hit[0] == items:
+                return hit[1], hit[2], n
+        except TypeError:
+            items = None
         cols = (C.c_int * max(n, 1))()
         vals = (C.c_double * max(n, 1))()
         for k, (name, value) in enumerate(stimulus.items()):
             cols[k] = self.ode.parameter_indices(name)                 # odeSolver.py:112
             vals[k] = float(value)
+        if items is not None:
+            self._stim_cache = (items, cols, vals)
         return cols, vals, n
 
     def _mask(self, locator):
@@ -747,14 +770,16 @@ class MembraneModel:
             # answers the same on a sample of rows: a locator that closes over something the
             # caller changes (a moving stimulus region) is re-evaluated, not served stale.
             # `strict_locators=True` re-evaluates every row every time.
-            if self._same_on_sample(locator, hit[1], hit[2]):
+            if self._same_on_sample(locator, hit[1], hit[2], hit[3]):
                 return hit[1]
         mask, vectorised = self._rows_of(locator, tell=True)
         if mask.all():
             mask = None        # every row selected: same as no locator
         if len(self._mask_cache) >= _MASK_CACHE_ENTRIES:     # a caller that builds a new lambda
             self._mask_cache.pop(next(iter(self._mask_cache)))   # per step must not pile up masks
-        self._mask_cache[id(locator)] = (locator, mask, vectorised)
+        rows = self._sample()[0]
+        want = np.ones(len(rows), dtype=bool) if mask is None else mask[rows]
+        self._mask_cache[id(locator)] = (locator, mask, vectorised, want)
         return mask
 
     def _sample(self):
@@ -767,14 +792,15 @@ class MembraneModel:
             smp = self._sample_rows_cache = (rows, Xs, np.ascontiguousarray(Xs.T), self.nodes)
         return smp
 
-    def _same_on_sample(self, locator, cached, vectorised):
+    def _same_on_sample(self, locator, cached, vectorised, want=None):
         rows, Xs, XsT, _ = self._sample()
-        want = np.ones(len(rows), dtype=bool) if cached is None else cached[rows]
+        if want is None:
+            want = np.ones(len(rows), dtype=bool) if cached is None else cached[rows]
         if vectorised:                      # one call on the [gdim, k] sample instead of k calls
             try:
-                r = np.asarray(locator(XsT))
-                if r.shape == want.shape and r.dtype == np.bool_:
-                    return bool(np.array_equal(r, want))
+                r = locator(XsT)
+                if type(r) is np.ndarray and r.shape == want.shape and r.dtype == np.bool_:
+                    return bool((r == want).all())
             except Exception:
                 pass
         return all(bool(locator(Xs[k])) == bool(want[k]) for k in range(len(rows)))
@@ -832,25 +858,29 @@ class MembraneModel:
     def _set_column(self, kind, col, src):
         self._pending.pop((kind, col), None)            # a recorded write to this column is superseded
         self._prefetched.pop((kind, col), None)         # ... and what the step wrote back is stale
-        check(self._lib.kem_set_column(self._h, kind, col, src.ctypes.data, self.nodes), "kem_set_column")
+        check(self._lib.kem_set_column(self._h, kind, col, _cabi.address(src), self.nodes), "kem_set_column")
 
     def _get_column(self, kind, col, dst):
         self._flush_pending()
-        check(self._lib.kem_get_column(self._h, kind, col, dst.ctypes.data, self.nodes), "kem_get_column")
+        check(self._lib.kem_get_column(self._h, kind, col, _cabi.address(dst), self.nodes), "kem_get_column")
         self._settle()
 
     # --- Work horses (odeSolver.py:130-188)
     def __set_ODE(self, what, which, u, locator=None):
         '''ODE setting '''
         kind, col = self._kind_col(what, which)
-        mask = self._mask(locator)
-        full = np.asarray(u.x.array)
-        source = np.ascontiguousarray(full[:self.nodes], dtype=np.float64)
+        mask = None if locator is None else self._mask(locator)
+        full = u.x.array
+        if type(full) is np.ndarray and full.dtype == np.float64 and full.ndim == 1 and full.flags.c_contiguous:
+            source = full                  # the library reads the first `nodes` entries in place
+        else:
+            full = np.asarray(full)
+            source = np.ascontiguousarray(full[:self.nodes], dtype=np.float64)
         if len(source) < self.nodes:
             raise IndexError(f"u.x.array has {len(source)} entries, the membrane has {self.nodes} DOFs")
         if self.nodes == 0:
             return self.states
-        pinned = self.auto_register and _HOST_CACHE.sight(u, full)
+        pinned = self.auto_register and full.nbytes >= _HOST_CACHE.min_bytes and _HOST_CACHE.sight(u, full)
         if mask is None:
             if self.exchange == "deferred" and (pinned or _cabi.host_is_pinned(source)):
                 # only recorded: copied by the next step, pipelined with the kernel
@@ -858,7 +888,11 @@ class MembraneModel:
                 self._prefetched.pop((kind, col), None)
                 self._pending[(kind, col)] = (source, u)
             else:
-                self._set_column(kind, col, source)
+                if self._pending or self._prefetched:
+                    self._pending.pop((kind, col), None)
+                    self._prefetched.pop((kind, col), None)
+                check(self._lib.kem_set_column(self._h, kind, col, _cabi.address(source), self.nodes),
+                      "kem_set_column")
         elif mask.any():
             self._flush_pending()
             m8 = np.ascontiguousarray(mask, dtype=np.uint8)
@@ -869,7 +903,7 @@ class MembraneModel:
     def __get_PDE(self, what, which, u, locator=None):
         '''Update PDE potentials from the ODE solver'''
         kind, col = self._kind_col(what, which)
-        mask = self._mask(locator)
+        mask = None if locator is None else self._mask(locator)
         if self.nodes == 0:
             return u
         dest = u.x.array
@@ -877,16 +911,21 @@ class MembraneModel:
                   and dest.ndim == 1 and dest.flags.c_contiguous and dest.flags.writeable
                   and len(dest) >= self.nodes)
         if direct:
-            pinned = self.auto_register and _HOST_CACHE.sight(u, dest)
+            pinned = self.auto_register and dest.nbytes >= _HOST_CACHE.min_bytes and _HOST_CACHE.sight(u, dest)
             if self.exchange == "deferred":
-                if self._prefetched.pop((kind, col), None) == (dest.ctypes.data, dest.nbytes) and not self._pending:
+                if self._prefetched.pop((kind, col), None) == (_cabi.address(dest), dest.nbytes) and not self._pending:
                     # the running step is writing this column into this very array: wait for it
                     self._bound_out[(kind, col)] = (dest, u)
                     self._wait_exchange()
                     return u
                 if pinned or _cabi.host_is_pinned(dest):
                     self._bound_out[(kind, col)] = (dest, u)    # the next step writes it back itself
-            self._get_column(kind, col, dest)
+            if self._pending:
+                self._flush_pending()
+            check(self._lib.kem_get_column(self._h, kind, col, _cabi.address(dest), self.nodes),
+                  "kem_get_column")
+            if self._status_pending:
+                self._settle()
             return u
         tmp = np.empty(self.nodes, dtype=np.float64)
         self._get_column(kind, col, tmp)
