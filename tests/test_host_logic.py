@@ -233,3 +233,93 @@ def test_eliminated_ion_terms_follow_the_reference_expression():
     with pytest.raises(Exception):
         from knpemi_b200.device_updates import _pack
         _pack([(1.0, 8)] * 9)
+
+
+def test_address_is_the_data_pointer_for_every_kind_of_array():
+    from knpemi_b200._cabi import address
+    a = np.arange(32.0)
+    ro = a.copy()
+    ro.setflags(write=False)
+    for arr in (a, a[3:], a[::2], ro, np.zeros(0), np.zeros((4, 3))[1]):
+        assert address(arr) == arr.ctypes.data
+
+
+class _RecordingLib:
+    """Records what the setters, getters and the step hand to the library (no device here)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def kem_set_column(self, h, kind, col, ptr, n):
+        self.calls.append(("set", kind, col, int(ptr), n))
+        return 0
+
+    def kem_get_column(self, h, kind, col, ptr, n):
+        self.calls.append(("get", kind, col, int(ptr), n))
+        return 0
+
+    def kem_set_stimulus_mask(self, h, ptr, n):
+        self.calls.append(("mask", None if ptr is None else int(ptr), n))
+        return 0
+
+    def kem_step(self, h, t, dt, n_sub, scheme, n_stim, cols, vals, flags):
+        self.calls.append(("step", t, dt, n_sub, [cols[k] for k in range(n_stim)],
+                           [vals[k] for k in range(n_stim)]))
+        return 0
+
+    def kem_last_error(self):
+        return b""
+
+
+def recording_model(n=300):
+    import ctypes as C
+    from collections import OrderedDict
+    from knpemi_b200.models import hh_ideal
+    m = bare_model(n)
+    m.ode, m._lib, m._h = hh_ideal, _RecordingLib(), C.c_void_p(1)
+    m.exchange, m.auto_register, m.verbose = "immediate", True, False
+    m._pending, m._bound_out, m._prefetched = OrderedDict(), OrderedDict(), {}
+    m._status_pending, m.states, m.n_sub, m._scheme_id, m.time = False, None, 25, 0, 0.0
+    m._stim_mask_key, m._col_cache, m._stim_cache = "unset", {}, None
+    return m
+
+
+def test_the_call_sequence_hands_the_callers_own_arrays_and_current_stimulus_to_the_library():
+    """The cached column lookups and stimulus arguments (what keeps a setter under 2 us) must
+    not outlive a change of name, value or array."""
+    from ducks_for_tests import Func
+    m = recording_model()
+    ode, lib = m.ode, m._lib
+    u, v = Func(np.zeros(m.nodes)), Func(np.ones(m.nodes))
+    for _ in range(2):
+        m.set_parameter("K_e", u)
+        m.set_parameter("K_e", v)
+        m.get_parameter("I_ch_Na", u)
+        m.set_membrane_potential(v)
+    k_e, i_na, V = ode.parameter_indices("K_e"), ode.parameter_indices("I_ch_Na"), ode.state_indices("V")
+    want = [("set", k_e, u.x.array.ctypes.data), ("set", k_e, v.x.array.ctypes.data),
+            ("get", i_na, u.x.array.ctypes.data), ("set", V, v.x.array.ctypes.data)] * 2
+    assert [(c[0], c[2], c[3]) for c in lib.calls] == want
+    assert {c[1] for c in lib.calls if c[2] == V} != {c[1] for c in lib.calls if c[2] == k_e}   # state vs parameter
+    with pytest.raises(ValueError):
+        m.set_parameter("no_such_parameter", u)
+    with pytest.raises(ValueError):
+        m.get_state("no_such_state", u)
+
+    lib.calls.clear()
+    loc = lambda x: x[0] < 0.4                                  # noqa: E731
+    m.step_lsoda(0.1, {"stim_amplitude": 10.0}, loc)
+    m.step_lsoda(0.1, {"stim_amplitude": 10.0}, loc)            # same arguments: cached, mask not re-sent
+    m.step_lsoda(0.1, {"stim_amplitude": 7.5}, loc)             # new value
+    m.step_lsoda(0.1, {"g_K_bar": 7.5}, loc)                    # new name
+    m.step_lsoda(0.1, {"stim_amplitude": 1.0, "g_K_bar": 2.0}, None)
+    m.step_lsoda(0.1, None)
+    steps = [c for c in lib.calls if c[0] == "step"]
+    amp, gk = ode.parameter_indices("stim_amplitude"), ode.parameter_indices("g_K_bar")
+    assert [(s[4], s[5]) for s in steps] == [([amp], [10.0]), ([amp], [10.0]), ([amp], [7.5]), ([gk], [7.5]),
+                                             ([amp, gk], [1.0, 2.0]), ([], [])]
+    assert [round(s[1], 12) for s in steps] == [0.0, 0.1, 0.2, 0.3, 0.4, 0.5]
+    masks = [c for c in lib.calls if c[0] == "mask"]
+    assert len(masks) == 2 and masks[0][1] is not None and masks[1][1] is None   # locator once, then "every row"
+    with pytest.raises(ValueError):
+        m.step_lsoda(0.1, {"no_such_parameter": 1.0})
