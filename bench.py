@@ -97,6 +97,14 @@ class ClockSampler:
             return
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
+        # nvidia-smi needs 0.1-0.5 s before its first row; a timed region of 30 steps (0.15 s) that
+        # starts earlier can end without a single sample
+        self._wait(lambda: bool(self.rows), 3.0)
+
+    def _wait(self, done, timeout):
+        t_end = time.perf_counter() + timeout
+        while not done() and time.perf_counter() < t_end and self.proc.poll() is None:
+            time.sleep(0.005)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -105,7 +113,7 @@ class ClockSampler:
     def stop(self, t0: float, t1: float) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        time.sleep(0.06)
+        self._wait(lambda: bool(self.rows) and self.rows[-1][0] > t1, 0.5)   # the sample that closes the region
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -113,9 +121,12 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ts, line in self.rows:
-            if not (t0 <= ts <= t1 + 0.06):
-                continue
+        rows = list(self.rows)
+        inside = [r for r in rows if t0 <= r[0] <= t1 + 0.06]
+        bracketing = not inside
+        if bracketing:      # region shorter than one sampling period: the samples either side of it
+            inside = [r for r in rows if r[0] < t0][-1:] + [r for r in rows if r[0] > t1][:1]
+        for ts, line in inside:
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 8:
                 continue
@@ -131,7 +142,8 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(smax) if smax else None,
                 "power_w_max": max(power) if power else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                **({"bracketing_samples": True} if bracketing and sm else {})}
 
 
 class Dist:

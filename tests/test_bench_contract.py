@@ -51,3 +51,46 @@ def test_gpu_arm_refuses_to_run_without_a_device():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                        timeout=300)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def _bench_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_clock_sampler_has_samples_for_a_region_shorter_than_its_start_up(tmp_path, monkeypatch):
+    """`nvidia-smi` needs a few hundred ms before its first row and samples every 50 ms; the default
+    timed region is 0.15 s.  The `clocks` object must still carry samples (a line without them is
+    rejected), from inside the region or, when it is shorter than a period, either side of it."""
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nsleep 0.4\nwhile true; do\n"
+                    "echo '0, 1965, 1965, 300.5, Not Active, Not Active, Not Active, Active'; sleep 0.05; done\n")
+    fake.chmod(0o755)
+    monkeypatch.setenv("PATH", f"{tmp_path}:{os.environ['PATH']}")
+    bench = _bench_module()
+    for seconds in (0.15, 0.005):
+        s = bench.ClockSampler(0)
+        s.start()
+        t0 = time.perf_counter()
+        time.sleep(seconds)
+        got = s.stop(t0, time.perf_counter())
+        assert got["samples"] >= 1 and got["sm_mhz"] == 1965.0 and got["sm_max_mhz"] == 1965.0
+        assert got["reasons"] == ["sw_power_cap"]
+
+
+def test_clock_sampler_without_nvidia_smi_reports_no_samples(tmp_path, monkeypatch):
+    monkeypatch.setenv("PATH", str(tmp_path))                   # no nvidia-smi anywhere
+    bench = _bench_module()
+    s = bench.ClockSampler(0)
+    s.start()
+    assert s.stop(0.0, 1.0)["samples"] == 0
+    dead = tmp_path / "nvidia-smi"                              # one that exits at once
+    dead.write_text("#!/bin/sh\nexit 3\n")
+    dead.chmod(0o755)
+    s = bench.ClockSampler(0)
+    s.start()
+    assert s.stop(0.0, 1.0)["samples"] == 0
