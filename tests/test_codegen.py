@@ -430,3 +430,37 @@ def test_relaxed_gate_form_is_the_same_function():
         dy1, p1 = evaluate(pm, 0.0, y, list(p))
         dy2, p2 = evaluate(pm2, 0.0, y, list(p))
         assert np.allclose(dy1, dy2, rtol=1e-15, atol=1e-15) and p1[1] == p2[1]
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_model_source_parses_to_what_python_computes(seed, tmp_path):
+    """Parser and DAG against CPython itself: the random straight-line models of the GPU
+    differential test (`test_gpu_random_models.py`, which compares the kernel with the DAG
+    interpreter) are executed as ordinary Python and compared with the interpreter, so a parse
+    error (precedence, sign, a wrong dependency class, a mis-lowered call) cannot hide on both
+    sides of that test.  Not bit-for-bit: the interpreter follows numba (`x**3` by squaring),
+    CPython calls libm `pow`."""
+    import importlib.util
+    from test_gpu_random_models import NP, NS, random_model_source
+    from knpemi_b200.codegen import parse_model_source
+    from knpemi_b200.codegen.interpret import evaluate
+    src = random_model_source(seed)
+    path = tmp_path / f"mm_random_{seed}.py"
+    path.write_text(src)
+    spec = importlib.util.spec_from_file_location(path.stem, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    pm = parse_model_source(src, filename=str(path))
+    rng = np.random.default_rng(1000 + seed)
+    worst = 0.0
+    for t in (0.0, 0.31, 0.69, 0.71, 0.92, 0.94, 1.5):             # both sides of mod(t, 0.7) and t < 0.93
+        y = rng.uniform(-1, 1, NS)
+        p = mod.init_parameter_values()
+        p[:3] = rng.uniform(-1, 1, 3)
+        p_py, dy_py = p.copy(), np.zeros(NS)
+        mod.rhs_numba(t, y.copy(), dy_py, p_py)
+        dy, p_after = evaluate(pm, t, list(y), list(p))
+        got, want = np.array(list(dy) + list(p_after)), np.concatenate([dy_py, p_py])
+        assert len(p_after) == NP
+        worst = max(worst, float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-3))))
+    assert worst < 1e-12, worst
